@@ -1,0 +1,184 @@
+/*
+ * ycnr_als.h — C ABI of the B200 (sm_100a) explicit-ALS factor-update library
+ * (libycnr_als.so).  Plain pointers and sizes only; this is exactly the surface the
+ * reference's native addon slot binds (N-API shim: you_can_not_recommend_b200/napi/,
+ * ctypes: you_can_not_recommend_b200/native.py).  There is NO CPU fallback: every
+ * compute entry point fails with a non-zero status when no CUDA device is usable.
+ *
+ * What each entry point replaces in the reference (file:line into upstream):
+ *
+ *   ycnr_create / ycnr_destroy ........ EmfWorker.mw_prepareToTrain / mw_endTrain
+ *                                       (lib/emf/EmfWorker.js:119-130,160-164), options
+ *                                       lib/emf/EmfBase.js:52-140
+ *   ycnr_attach_factors ............... EmfBase.openSharedFactors (EmfBase.js:430-450):
+ *                                       the row-major Float32 user/item matrices in SysV shm
+ *   ycnr_start_train_step ............. EmfWorker.mw_startTrainStep (EmfWorker.js:135-138)
+ *   ycnr_als_portion .................. EmfWorker.mw_calcTrainAlsPortion (EmfWorker.js:169-261)
+ *                                       incl. EmfBase.copySubFixedFactors (EmfBase.js:537-555),
+ *                                       BLAS.gemm / Matrix.add / multiply / solveSquare / transpose
+ *                                       (EmfWorker.js:231-247) and the in-place row write
+ *                                       (EmfBase.js:518-532)
+ *   ycnr_end_train_step ............... the 'stepComplete' barrier (EmfMaster.js:776-785)
+ *   ycnr_start_calc_rmse .............. EmfWorker.mw_startCalcRmse (EmfWorker.js:144-148)
+ *   ycnr_rmse_portion ................. EmfWorker.mw_calcRmsePortion (EmfWorker.js:266-315)
+ *                                       incl. predictSync/_alsPredict (EmfBase.js:785-827)
+ *   ycnr_s_als_build_sub_fixed_facts .. sAlsBuildSubFixedFacts (cpp_utils/als_utils.cc:22-38,
+ *                                       registered cpp_utils/cpp_utils.cc:3-8)
+ *   ycnr_rowset_* / ycnr_als_rowset / ycnr_rmse_rowset
+ *                                       bulk form of the same two portion calls: all portions
+ *                                       of a step resident on the device
+ *   ycnr_device_factors, ycnr_ipc_*, ycnr_set_peers
+ *                                       replica refresh after a half-step, replacing
+ *                                       'alsSaveCalcedFactors' streams (EmfMaster.js:711-723)
+ *
+ * Conventions: ids 0-based; factor matrices row-major [rows x factors_count] float32
+ * (EmfBase.js:403-412); every function returns 0 on success, otherwise a non-zero
+ * code with a message in ycnr_last_error() (the N-API shim turns it into a thrown
+ * Error so the worker's uncaughtException path fires, EmfWorkerProcess.js:30-45).
+ * Calls are blocking with respect to their INPUT buffers (the caller may reuse
+ * them on return) and one call is in flight per context, like the reference worker.
+ */
+#ifndef YCNR_ALS_H
+#define YCNR_ALS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ycnr_ctx ycnr_ctx;
+
+/* stepType (EmfWorker.js:135-148) */
+enum {
+  YCNR_BY_USER = 0,       /* solve user rows, item factors fixed */
+  YCNR_BY_ITEM = 1,       /* solve item rows, user factors fixed */
+  YCNR_RMSE_VALIDATE = 2,
+  YCNR_RMSE_TEST = 3
+};
+
+/* which matrix */
+enum { YCNR_USER_FACTORS = 0, YCNR_ITEM_FACTORS = 1 };
+
+/* Gram-build code path (north star: tensor cores via 3xTF32 or FP32 FFMA) */
+enum { YCNR_GRAM_AUTO = 0, YCNR_GRAM_FFMA = 1, YCNR_GRAM_TC3XTF32 = 2 };
+
+typedef struct ycnr_options {
+  int32_t factors_count;        /* options.factorsCount (EmfBase.js:90) */
+  int32_t total_users;          /* user matrix height = max(list_id) (EmfLord.js:81) */
+  int32_t total_items;          /* item matrix height = max(id) (EmfLord.js:82) */
+  double user_fact_reg;         /* options.als.userFactReg (EmfBase.js:67) */
+  double item_fact_reg;         /* options.als.itemFactReg (EmfBase.js:69) */
+  int32_t use_double_precision; /* options.useDoublePrecision: must be 0 (rejected otherwise) */
+  int32_t lowmem;               /* options.lowmem: must be 0 (rejected otherwise) */
+  int32_t device;               /* CUDA device ordinal */
+  int32_t gram_path;            /* YCNR_GRAM_* */
+  int32_t dual_max_cols;        /* rows with <= this many ratings solve the n x n dual system;
+                                   -1 = library default, 0 = never */
+  int32_t split_cols;           /* ratings per partial-Gram work item for long rows; 0 = default */
+  int32_t profile;              /* record CUDA events around every kernel class */
+  int32_t reserved[4];
+} ycnr_options;
+
+/* 'completedPortion' message fields (EmfWorker.js:254-260, 304-314) */
+typedef struct ycnr_portion_info {
+  int32_t rows_from;            /* rowsRange.from = first row id of the portion (-1 if empty) */
+  int32_t rows_cnt;             /* rowsRange.cnt  = rowsInPortion */
+  int64_t ratings_in_portion;   /* sum of cols */
+  double time_ms;               /* host wall time spent inside the call */
+  double r_sum_diff2;           /* RMSE only */
+  double r_cnt;
+  double r_sum;
+} ycnr_portion_info;
+
+/* accumulated device time per kernel class since the last ycnr_profile_reset */
+enum {
+  YCNR_K_PRIMAL_FUSED = 0,   /* gather + Gram + RHS + ridge + Cholesky solve, one CTA per row */
+  YCNR_K_DUAL_FUSED = 1,     /* gather + n x n Gram + Cholesky solve + Y^T z */
+  YCNR_K_GRAM_PARTIAL = 2,   /* gather + partial Gram/RHS of one slice of a long row */
+  YCNR_K_REDUCE_SOLVE = 3,   /* sum partials + ridge + Cholesky solve */
+  YCNR_K_RMSE_ROWS = 4,
+  YCNR_K_RMSE_REDUCE = 5,
+  YCNR_K_GATHER = 6,
+  YCNR_K_GRAM_TC = 7,        /* tcgen05 3xTF32 Gram */
+  YCNR_K_CLASSES = 8
+};
+typedef struct ycnr_profile {
+  double ms[YCNR_K_CLASSES];
+  int64_t launches[YCNR_K_CLASSES];
+  int64_t rows[YCNR_K_CLASSES];      /* rows (or work items) processed */
+  int64_t ratings[YCNR_K_CLASSES];   /* ratings gathered */
+  int64_t total_launches;            /* every kernel launched by this context, profiled or not */
+} ycnr_profile;
+
+const char* ycnr_last_error(void);
+int ycnr_device_count(int32_t* count_out);
+
+int ycnr_create(const ycnr_options* opts, ycnr_ctx** ctx_out);
+int ycnr_destroy(ycnr_ctx* ctx);
+
+/* ---- factor store --------------------------------------------------------- */
+/* Borrow the two host matrices (pointers into the shm segments), page-lock them and
+ * upload both to the device replicas.  The pointers stay owned by the caller and must
+ * outlive the context (or until the next attach). */
+int ycnr_attach_factors(ycnr_ctx* ctx, float* user_factors, float* item_factors);
+int ycnr_upload_factors(ycnr_ctx* ctx, int32_t which);                     /* host -> device */
+int ycnr_download_factors(ycnr_ctx* ctx, int32_t which, int32_t row_from, int32_t row_cnt); /* device -> host */
+/* Tell the library another process changed the host copy (next step re-uploads it). */
+int ycnr_invalidate_device(ycnr_ctx* ctx, int32_t which);
+/* Raw device pointer of a replica (for the NCCL all-gather done by the host layer). */
+int ycnr_device_factors(ycnr_ctx* ctx, int32_t which, void** dptr_out);
+int ycnr_stream(ycnr_ctx* ctx, void** cuda_stream_out);
+int ycnr_synchronize(ycnr_ctx* ctx);
+
+/* ---- drop-in per-portion path (reference wire format) ------ */
+int ycnr_start_train_step(ycnr_ctx* ctx, int32_t step_type);
+int ycnr_als_portion(ycnr_ctx* ctx, const int32_t* als_rows, const int32_t* als_indx,
+                     const float* als_vals, ycnr_portion_info* info_out);
+/* Barrier: waits for every queued portion and makes the solved rows visible in the
+ * attached host matrix. */
+int ycnr_end_train_step(ycnr_ctx* ctx);
+
+int ycnr_start_calc_rmse(ycnr_ctx* ctx, int32_t step_type, double global_avg_shift);
+int ycnr_rmse_portion(ycnr_ctx* ctx, const int32_t* rmse_rows, const int32_t* rmse_indx,
+                      const float* rmse_vals, ycnr_portion_info* info_out);
+
+/* cpp_utils.sAlsBuildSubFixedFacts(sub, fixed, indx, cols, k): sub[c,:] = fixed[indx[c],:].
+ * 'fixed' is a host matrix of fixed_rows x k floats. */
+int ycnr_s_als_build_sub_fixed_facts(ycnr_ctx* ctx, float* sub, const float* fixed, int64_t fixed_rows,
+                                     const int32_t* indx, int32_t cols, int32_t k);
+
+/* ---- bulk path: all portions of a step resident on the device ------------- */
+/* A row set is the concatenation of the portion headers of one step: row r covers
+ * indx/vals[row_start[r] .. row_start[r]+row_len[r]).  span = number of entries of
+ * indx/vals to upload.  portion_first[n_portions+1] indexes the row list (RMSE only
+ * needs it, for the per-portion sums of quirk Q7); may be NULL with n_portions = 0. */
+int ycnr_rowset_create(ycnr_ctx* ctx, int32_t step_type, int32_t n_rows, const int32_t* row_ids,
+                       const int64_t* row_start, const int32_t* row_len,
+                       const int32_t* indx, const float* vals, int64_t span,
+                       const int32_t* portion_first, int32_t n_portions, int32_t* rowset_out);
+int ycnr_rowset_destroy(ycnr_ctx* ctx, int32_t rowset);
+/* One half-step over the row set, asynchronous on the context stream; device replicas
+ * only (use ycnr_download_factors for the host copy). */
+int ycnr_als_rowset(ycnr_ctx* ctx, int32_t rowset);
+/* totals[3] = {rSumDiff2, rCnt, rSum}; portion_sums[n_portions*3] optional. Synchronous. */
+int ycnr_rmse_rowset(ycnr_ctx* ctx, int32_t rowset, double global_avg_shift, double* totals,
+                     double* portion_sums);
+
+/* ---- multi-GPU replica refresh over NVLink peer memory --------------------- */
+/* 64-byte CUDA IPC handle of a device replica; import returns a peer-mapped pointer. */
+int ycnr_ipc_export(ycnr_ctx* ctx, int32_t which, uint8_t handle_out[64]);
+int ycnr_ipc_import(ycnr_ctx* ctx, const uint8_t handle[64], void** dptr_out);
+int ycnr_ipc_close(ycnr_ctx* ctx, void* dptr);
+/* Peer replicas of matrix 'which': the solve kernels store every solved row into each of
+ * them as well (fused all-gather).  n_peers = 0 clears. Max 7 peers. */
+int ycnr_set_peers(ycnr_ctx* ctx, int32_t which, int32_t n_peers, void* const* peer_dptrs);
+
+/* ---- measurement ------------------------------------------------------------ */
+int ycnr_profile_reset(ycnr_ctx* ctx);
+int ycnr_profile_read(ycnr_ctx* ctx, ycnr_profile* out);   /* synchronises the stream */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YCNR_ALS_H */

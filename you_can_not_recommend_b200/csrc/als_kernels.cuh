@@ -1,0 +1,485 @@
+// als_kernels.cuh — FP32 (FFMA) explicit-ALS row update kernels for sm_100a.
+//
+// One CTA owns one row (user or item) of the solved side and performs the whole
+// reference loop body (lib/emf/EmfWorker.js:214-248) without touching HBM in between:
+//
+//   gather     Y[c,:] = F[indx[c],:]            EmfBase.js:537-555      cp.async -> smem tiles
+//   Gram       A = Y^T Y                        EmfWorker.js:231-232    4x4 register tiles, lower triangle
+//   ridge      A += (lambda*n) I                EmfWorker.js:233-235
+//   rhs        b = Y^T r                        EmfWorker.js:238-245    extra tile row of the same sweep
+//   solve      x = A^-1 b                       EmfWorker.js:246        tile Cholesky in registers
+//   write      S[rowId,:] = x                   EmfWorker.js:247        (+ NVLink peer replicas)
+//
+// Data layout: the k x k system lives in REGISTERS as 4x4 tiles of its lower triangle,
+// tile (I,L), L<=I, owned by thread t = I(I+1)/2+L; an additional tile row I = mt holds
+// the right-hand side, so the forward substitution happens inside the factorisation
+// (Cholesky of the bordered matrix [[A b],[b^T .]]).  Shared memory only carries the
+// gathered rows and a one-tile-column panel that is broadcast at every step.
+//
+// Rows with fewer ratings than factors use the dual system (als_dual_kernel):
+//   x = Y^T (Y Y^T + lambda*n I)^-1 r   ==   (Y^T Y + lambda*n I)^-1 Y^T r
+// an n x n solve instead of k x k — algebraically identical, ~(k/n)^3 cheaper.
+// Long rows are cut into slices (MODE_PARTIAL) whose tile partials are summed in a
+// fixed order by MODE_REDUCE, so results do not depend on scheduling.
+#pragma once
+#include "common.cuh"
+
+namespace ycnr {
+
+enum { MODE_FUSED = 0, MODE_PARTIAL = 1, MODE_REDUCE = 2 };
+
+constexpr int kStageRows = 32;  // ratings staged per smem tile in the primal kernels
+
+// linear tile index -> (I, L); t >= ntri addresses the right-hand-side tile row I = mt
+__device__ __forceinline__ void tile_coords(int t, int mt, int ntri, int& I, int& L) {
+  if (t < ntri) {
+    int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (i * (i + 1) / 2 > t) --i;
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    I = i;
+    L = t - i * (i + 1) / 2;
+  } else {
+    I = mt;
+    L = t - ntri;
+  }
+}
+
+// Cholesky of a symmetric 4x4 tile held in full; on return d holds M = L^-1 (lower
+// triangle, zeros above).  sqrtf and the divisions are IEEE (no fast-math).
+__device__ __forceinline__ void chol4_inverse(float (&d)[4][4]) {
+  const float l00 = sqrtf(d[0][0]);
+  const float i0 = 1.0f / l00;
+  const float l10 = d[1][0] * i0, l20 = d[2][0] * i0, l30 = d[3][0] * i0;
+  const float l11 = sqrtf(d[1][1] - l10 * l10);
+  const float i1 = 1.0f / l11;
+  const float l21 = (d[2][1] - l20 * l10) * i1;
+  const float l31 = (d[3][1] - l30 * l10) * i1;
+  const float l22 = sqrtf(d[2][2] - l20 * l20 - l21 * l21);
+  const float i2 = 1.0f / l22;
+  const float l32 = (d[3][2] - l30 * l20 - l31 * l21) * i2;
+  const float l33 = sqrtf(d[3][3] - l30 * l30 - l31 * l31 - l32 * l32);
+  const float i3 = 1.0f / l33;
+  const float m10 = -(l10 * i0) * i1;
+  const float m21 = -(l21 * i1) * i2;
+  const float m32 = -(l32 * i2) * i3;
+  const float m20 = -(l20 * i0 + l21 * m10) * i2;
+  const float m31 = -(l31 * i1 + l32 * m21) * i3;
+  const float m30 = -(l30 * i0 + l31 * m10 + l32 * m20) * i3;
+  d[0][0] = i0;  d[0][1] = 0.f; d[0][2] = 0.f; d[0][3] = 0.f;
+  d[1][0] = m10; d[1][1] = i1;  d[1][2] = 0.f; d[1][3] = 0.f;
+  d[2][0] = m20; d[2][1] = m21; d[2][2] = i2;  d[2][3] = 0.f;
+  d[3][0] = m30; d[3][1] = m31; d[3][2] = m32; d[3][3] = i3;
+}
+
+// Blocked right-looking Cholesky + both triangular solves on register tiles.
+//   acc[q]  : tile (tI[q], tL[q]) of the bordered system; tI = tL = -1 marks "no tile".
+//   panel   : (mt+1)*16 floats, dinv: 16 floats, ysm: 4*mt floats of shared memory.
+// On return ysm[0 .. 4*mt) holds the solution.  All threads of the CTA must call.
+template <int TPT>
+__device__ __forceinline__ void tile_cholesky_solve(float (&acc)[TPT][4][4], const int (&tI)[TPT],
+                                                    const int (&tL)[TPT], int mt, float* panel, float* dinv,
+                                                    float* ysm) {
+  for (int J = 0; J < mt; ++J) {
+    // (a) factor the diagonal tile, publish M = L_JJ^-1
+#pragma unroll
+    for (int q = 0; q < TPT; ++q) {
+      if (tI[q] == J && tL[q] == J) {
+        chol4_inverse(acc[q]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(dinv + 4 * i) = make_float4(acc[q][i][0], acc[q][i][1], acc[q][i][2], acc[q][i][3]);
+      }
+    }
+    __syncthreads();
+    // (b) panel: X_IJ = A_IJ * L_JJ^-T  (rows I > J, including the rhs row I = mt)
+#pragma unroll
+    for (int q = 0; q < TPT; ++q) {
+      if (tL[q] == J && tI[q] > J) {
+        float m[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(dinv + 4 * i);
+          m[i][0] = v.x; m[i][1] = v.y; m[i][2] = v.z; m[i][3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a0 = acc[q][i][0], a1 = acc[q][i][1], a2 = acc[q][i][2], a3 = acc[q][i][3];
+          const float x0 = a0 * m[0][0];
+          const float x1 = fmaf(a1, m[1][1], a0 * m[1][0]);
+          const float x2 = fmaf(a2, m[2][2], fmaf(a1, m[2][1], a0 * m[2][0]));
+          const float x3 = fmaf(a3, m[3][3], fmaf(a2, m[3][2], fmaf(a1, m[3][1], a0 * m[3][0])));
+          acc[q][i][0] = x0; acc[q][i][1] = x1; acc[q][i][2] = x2; acc[q][i][3] = x3;
+          *reinterpret_cast<float4*>(panel + 16 * tI[q] + 4 * i) = make_float4(x0, x1, x2, x3);
+        }
+      }
+    }
+    __syncthreads();
+    // (c) trailing update: A_IL -= X_IJ * X_LJ^T for J < L <= I
+#pragma unroll
+    for (int q = 0; q < TPT; ++q) {
+      if (tL[q] > J) {
+        float xi[4][4], xl[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(panel + 16 * tI[q] + 4 * i);
+          xi[i][0] = v.x; xi[i][1] = v.y; xi[i][2] = v.z; xi[i][3] = v.w;
+          const float4 w = *reinterpret_cast<const float4*>(panel + 16 * tL[q] + 4 * i);
+          xl[i][0] = w.x; xl[i][1] = w.y; xl[i][2] = w.z; xl[i][3] = w.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float s = acc[q][i][j];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s = fmaf(-xi[i][c], xl[j][c], s);
+            acc[q][i][j] = s;
+          }
+      }
+    }
+    // the next (a) only touches the owner's own registers and dinv, whose readers all
+    // passed the barrier after (b); panel is rewritten only after the barrier after (a).
+  }
+  // y = L^-1 b sits in row 0 of the rhs tiles
+#pragma unroll
+  for (int q = 0; q < TPT; ++q) {
+    if (tI[q] == mt && tL[q] >= 0)
+      *reinterpret_cast<float4*>(ysm + 4 * tL[q]) = make_float4(acc[q][0][0], acc[q][0][1], acc[q][0][2], acc[q][0][3]);
+  }
+  __syncthreads();
+  // back substitution L^T x = y, right-looking over tile rows
+  for (int I = mt - 1; I >= 0; --I) {
+#pragma unroll
+    for (int q = 0; q < TPT; ++q) {
+      if (tI[q] == I && tL[q] == I) {  // acc holds M = L_II^-1 ; x_I = M^T y_I
+        const float4 y = *reinterpret_cast<const float4*>(ysm + 4 * I);
+        const float x0 = fmaf(acc[q][3][0], y.w, fmaf(acc[q][2][0], y.z, fmaf(acc[q][1][0], y.y, acc[q][0][0] * y.x)));
+        const float x1 = fmaf(acc[q][3][1], y.w, fmaf(acc[q][2][1], y.z, acc[q][1][1] * y.y));
+        const float x2 = fmaf(acc[q][3][2], y.w, acc[q][2][2] * y.z);
+        const float x3 = acc[q][3][3] * y.w;
+        *reinterpret_cast<float4*>(ysm + 4 * I) = make_float4(x0, x1, x2, x3);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < TPT; ++q) {
+      if (tI[q] == I && tL[q] >= 0 && tL[q] < I) {  // y_L -= X_IL^T x_I
+        const float4 x = *reinterpret_cast<const float4*>(ysm + 4 * I);
+        float4 y = *reinterpret_cast<const float4*>(ysm + 4 * tL[q]);
+        y.x -= acc[q][0][0] * x.x + acc[q][1][0] * x.y + acc[q][2][0] * x.z + acc[q][3][0] * x.w;
+        y.y -= acc[q][0][1] * x.x + acc[q][1][1] * x.y + acc[q][2][1] * x.z + acc[q][3][1] * x.w;
+        y.z -= acc[q][0][2] * x.x + acc[q][1][2] * x.y + acc[q][2][2] * x.z + acc[q][3][2] * x.w;
+        y.w -= acc[q][0][3] * x.x + acc[q][1][3] * x.y + acc[q][2][3] * x.z + acc[q][3][3] * x.w;
+        *reinterpret_cast<float4*>(ysm + 4 * tL[q]) = y;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Primal kernels: k x k system, KT = tiles per dimension (4*KT >= k), NT threads,
+// TPT tiles per thread.
+// ------------------------------------------------------------------------------------
+struct PrimalArgs {
+  RowsView rows;
+  const float* __restrict__ fixed;  // F, row-major, k columns
+  int k;
+  double lambda;
+  DstList dst;                      // S replicas
+  const int32_t* __restrict__ work; // MODE_FUSED/REDUCE: row index per CTA
+  // slices of long rows
+  const int32_t* __restrict__ item_row;   // MODE_PARTIAL: row index per work item
+  const int32_t* __restrict__ item_off;   // MODE_PARTIAL: first rating of the slice inside the row
+  int split_cols;                         // slice length
+  float* __restrict__ partial;            // [items][tiles][16]
+  const int32_t* __restrict__ row_first_item;  // MODE_REDUCE: per work entry
+  const int32_t* __restrict__ row_n_items;
+};
+
+template <int KT, int NT, int TPT, int MODE>
+__global__ void __launch_bounds__(NT) als_primal_kernel(const PrimalArgs a) {
+  constexpr int KP = 4 * KT;          // padded system size
+  constexpr int PITCH = KP + 4;       // + (val, 0, 0, 0): the rhs tile row reads its "a" operand here
+  constexpr int NTRI = KT * (KT + 1) / 2;
+  constexpr int NTILES = NTRI + KT;
+  static_assert(NT * TPT >= NTILES, "not enough threads for the tile set");
+  __shared__ __align__(16) float Ys[(MODE == MODE_REDUCE) ? 1 : 2 * kStageRows * PITCH];
+  __shared__ __align__(16) float panel[(KT + 1) * 16];
+  __shared__ __align__(16) float dinv[16];
+  __shared__ __align__(16) float ysm[KP];
+
+  const int tid = threadIdx.x;
+  const int k = a.k;
+  int tI[TPT], tL[TPT];
+#pragma unroll
+  for (int q = 0; q < TPT; ++q) {
+    const int t = tid + q * NT;
+    if (t < NTILES) tile_coords(t, KT, NTRI, tI[q], tL[q]);
+    else { tI[q] = -1; tL[q] = -1; }
+  }
+  float acc[TPT][4][4];
+#pragma unroll
+  for (int q = 0; q < TPT; ++q)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[q][i][j] = 0.f;
+
+  int row;          // index into the row list
+  int64_t seg_beg;  // first rating of this CTA's slice
+  int seg_len;
+  if (MODE == MODE_PARTIAL) {
+    row = a.item_row[blockIdx.x];
+    const int off = a.item_off[blockIdx.x];
+    seg_beg = a.rows.row_start[row] + off;
+    seg_len = min(a.split_cols, a.rows.row_len[row] - off);
+  } else {
+    row = a.work[blockIdx.x];
+    seg_beg = a.rows.row_start[row];
+    seg_len = a.rows.row_len[row];
+  }
+
+  if (MODE != MODE_REDUCE) {
+    // ---- gather + Gram + rhs ------------------------------------------------------
+    const bool vec = (k & 3) == 0;
+    const int CH = k >> 2;
+    // pad columns stay zero for the whole kernel (never targeted by cp.async)
+    for (int q = tid; q < 2 * kStageRows * (PITCH - k); q += NT) {
+      const int r = q / (PITCH - k), c = k + q % (PITCH - k);
+      if (c != KP) Ys[r * PITCH + c] = 0.f;
+    }
+    auto stage = [&](int t0, int buf) {
+      float* base = Ys + buf * kStageRows * PITCH;
+      if (vec) {
+        for (int q = tid; q < kStageRows * CH; q += NT) {
+          const int r = q / CH, c = q - r * CH;
+          const bool ok = t0 + r < seg_len;
+          const int col = ok ? __ldg(a.rows.indx + seg_beg + t0 + r) : 0;
+          cp_async16(base + r * PITCH + 4 * c, a.fixed + (size_t)col * k + 4 * c, ok ? 16 : 0);
+        }
+      } else {
+        for (int q = tid; q < kStageRows * k; q += NT) {
+          const int r = q / k, c = q - r * k;
+          const bool ok = t0 + r < seg_len;
+          const int col = ok ? __ldg(a.rows.indx + seg_beg + t0 + r) : 0;
+          cp_async4(base + r * PITCH + c, a.fixed + (size_t)col * k + c, ok ? 4 : 0);
+        }
+      }
+      for (int r = tid; r < kStageRows; r += NT) {
+        const bool ok = t0 + r < seg_len;
+        cp_async4(base + r * PITCH + KP, a.rows.vals + seg_beg + (ok ? t0 + r : 0), ok ? 4 : 0);
+      }
+    };
+    int aoff[TPT], boff[TPT];
+#pragma unroll
+    for (int q = 0; q < TPT; ++q) {
+      aoff[q] = tI[q] < 0 ? 0 : 4 * tI[q];  // rhs row (tI == KT) reads (val,0,0,0) at column KP
+      boff[q] = tL[q] < 0 ? 0 : 4 * tL[q];
+    }
+    const int ntile = (seg_len + kStageRows - 1) / kStageRows;
+    if (ntile > 0) stage(0, 0);
+    cp_async_commit();
+    for (int t = 0; t < ntile; ++t) {
+      if (t + 1 < ntile) stage((t + 1) * kStageRows, (t + 1) & 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+      const float* yb = Ys + (t & 1) * kStageRows * PITCH;
+      const int rcount = min(kStageRows, seg_len - t * kStageRows);
+#pragma unroll 4
+      for (int r = 0; r < rcount; ++r) {
+        const float* yr = yb + r * PITCH;
+#pragma unroll
+        for (int q = 0; q < TPT; ++q) {
+          const float4 av = *reinterpret_cast<const float4*>(yr + aoff[q]);
+          const float4 bv = *reinterpret_cast<const float4*>(yr + boff[q]);
+          const float ar[4] = {av.x, av.y, av.z, av.w};
+          const float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[q][i][j] = fmaf(ar[i], br[j], acc[q][i][j]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  if (MODE == MODE_PARTIAL) {
+    float* out = a.partial + (size_t)blockIdx.x * NTILES * 16;
+#pragma unroll
+    for (int q = 0; q < TPT; ++q) {
+      const int t = tid + q * NT;
+      if (t < NTILES) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(out + (size_t)t * 16 + 4 * i) =
+              make_float4(acc[q][i][0], acc[q][i][1], acc[q][i][2], acc[q][i][3]);
+      }
+    }
+    return;
+  }
+
+  if (MODE == MODE_REDUCE) {
+    const int first = a.row_first_item[blockIdx.x];
+    const int nit = a.row_n_items[blockIdx.x];
+    for (int it = 0; it < nit; ++it) {  // fixed order => deterministic sums
+      const float* in = a.partial + (size_t)(first + it) * NTILES * 16;
+#pragma unroll
+      for (int q = 0; q < TPT; ++q) {
+        const int t = tid + q * NT;
+        if (t < NTILES) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(in + (size_t)t * 16 + 4 * i);
+            acc[q][i][0] += v.x; acc[q][i][1] += v.y; acc[q][i][2] += v.z; acc[q][i][3] += v.w;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- ridge (EmfWorker.js:233-235: lambda*n formed in double, stored as float) -------
+  const float lam = (float)(a.lambda * (double)a.rows.row_len[row]);
+#pragma unroll
+  for (int q = 0; q < TPT; ++q) {
+    if (tI[q] >= 0 && tI[q] == tL[q]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (4 * tI[q] + i < k) acc[q][i][i] += lam;
+        else acc[q][i][i] = 1.0f;  // padding rows/cols: identity block, solution 0
+      }
+    }
+  }
+  tile_cholesky_solve<TPT>(acc, tI, tL, KT, panel, dinv, ysm);
+
+  const int rowId = a.rows.row_ids[row];
+  for (int c = tid; c < k; c += NT) {
+    const float x = ysm[c];
+    for (int d = 0; d < a.dst.n; ++d) a.dst.p[d][(size_t)rowId * k + c] = x;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Dual kernel: rows with n <= 4*MT_MAX ratings, n x n system  G = Y Y^T + lambda*n I.
+// ------------------------------------------------------------------------------------
+struct DualArgs {
+  RowsView rows;
+  const float* __restrict__ fixed;
+  int k;
+  int pitch;  // floats per staged row, multiple of 4 with (pitch/4) odd => conflict-free LDS.128
+  double lambda;
+  DstList dst;
+  const int32_t* __restrict__ work;
+};
+
+template <int MT_MAX, int NT>
+__global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
+  constexpr int NMAX = 4 * MT_MAX;
+  static_assert(NT >= MT_MAX * (MT_MAX + 1) / 2 + MT_MAX, "not enough threads for the tile set");
+  extern __shared__ __align__(16) float dsm[];
+  float* Y = dsm;                              // [NMAX][pitch]
+  float* panel = Y + NMAX * a.pitch;           // (MT_MAX+1)*16
+  float* dinv = panel + (MT_MAX + 1) * 16;     // 16
+  float* ysm = dinv + 16;                      // NMAX
+  float* vs = ysm + NMAX;                      // NMAX
+
+  const int tid = threadIdx.x;
+  const int k = a.k, pitch = a.pitch;
+  const int K4 = (k + 3) & ~3;
+  const int row = a.work[blockIdx.x];
+  const int64_t beg = a.rows.row_start[row];
+  const int n = a.rows.row_len[row];
+  const int mt = (n + 3) >> 2;
+  const int np = 4 * mt;
+
+  // ---- gather the n rated rows of F -----------------------------------------------
+  if ((k & 3) == 0) {
+    const int CH = k >> 2;
+    for (int q = tid; q < np * CH; q += NT) {
+      const int r = q / CH, c = q - r * CH;
+      const bool ok = r < n;
+      const int col = ok ? __ldg(a.rows.indx + beg + r) : 0;
+      cp_async16(Y + r * pitch + 4 * c, a.fixed + (size_t)col * k + 4 * c, ok ? 16 : 0);
+    }
+  } else {
+    for (int q = tid; q < np * K4; q += NT) {
+      const int r = q / K4, c = q - r * K4;
+      const bool ok = r < n && c < k;
+      const int col = ok ? __ldg(a.rows.indx + beg + r) : 0;
+      cp_async4(Y + r * pitch + c, a.fixed + (size_t)col * k + (ok ? c : 0), ok ? 4 : 0);
+    }
+  }
+  for (int r = tid; r < np; r += NT) vs[r] = r < n ? __ldg(a.rows.vals + beg + r) : 0.f;
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- G tiles ------------------------------------------------------------------------
+  const int ntri = mt * (mt + 1) / 2;
+  int tI[1], tL[1];
+  if (tid < ntri + mt) tile_coords(tid, mt, ntri, tI[0], tL[0]);
+  else { tI[0] = -1; tL[0] = -1; }
+  float acc[1][4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[0][i][j] = 0.f;
+
+  if (tI[0] >= 0 && tI[0] < mt) {
+    const float* ya = Y + 4 * tI[0] * pitch;
+    const float* yb = Y + 4 * tL[0] * pitch;
+    for (int c = 0; c < K4; c += 4) {
+      float4 av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        av[i] = *reinterpret_cast<const float4*>(ya + i * pitch + c);
+        bv[i] = *reinterpret_cast<const float4*>(yb + i * pitch + c);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float s = acc[0][i][j];
+          s = fmaf(av[i].x, bv[j].x, s);
+          s = fmaf(av[i].y, bv[j].y, s);
+          s = fmaf(av[i].z, bv[j].z, s);
+          s = fmaf(av[i].w, bv[j].w, s);
+          acc[0][i][j] = s;
+        }
+    }
+    if (tI[0] == tL[0]) {
+      const float lam = (float)(a.lambda * (double)n);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (4 * tI[0] + i < n) acc[0][i][i] += lam;
+        else acc[0][i][i] = 1.0f;
+      }
+    }
+  } else if (tI[0] == mt) {
+    const float4 v = *reinterpret_cast<const float4*>(vs + 4 * tL[0]);
+    acc[0][0][0] = v.x; acc[0][0][1] = v.y; acc[0][0][2] = v.z; acc[0][0][3] = v.w;
+  }
+  tile_cholesky_solve<1>(acc, tI, tL, mt, panel, dinv, ysm);
+
+  // ---- x = Y^T z --------------------------------------------------------------------------
+  const int rowId = a.rows.row_ids[row];
+  for (int c = tid; c < k; c += NT) {
+    float x = 0.f;
+    for (int p = 0; p < n; ++p) x = fmaf(Y[p * pitch + c], ysm[p], x);
+    for (int d = 0; d < a.dst.n; ++d) a.dst.p[d][(size_t)rowId * k + c] = x;
+  }
+}
+
+// sub[c,:] = fixed[indx[c],:]  (cpp_utils/als_utils.cc:22-38)
+__global__ void gather_rows_kernel(float* __restrict__ sub, const float* __restrict__ fixed,
+                                   const int32_t* __restrict__ indx, int cols, int k) {
+  const int64_t total = (int64_t)cols * k;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e / k), f = (int)(e - (int64_t)c * k);
+    sub[e] = fixed[(size_t)indx[c] * k + f];
+  }
+}
+
+}  // namespace ycnr

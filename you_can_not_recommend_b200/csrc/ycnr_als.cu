@@ -1,0 +1,942 @@
+// ycnr_als.cu — C ABI of libycnr_als.so (include/ycnr_als.h): context, factor store,
+// per-portion and bulk (row set) drivers, launch dispatch, profiling.
+// Kernels: als_kernels.cuh (FFMA primal/dual), gram_tc.cuh (tcgen05 3xTF32 Gram),
+// rmse_kernels.cuh.  sm_100a only; no CPU fallback anywhere in this file.
+#include "ycnr_als.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "als_kernels.cuh"
+#include "rmse_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[1024] = "";
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define CU(expr)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+  } while (0)
+#define OK(expr)          \
+  do {                    \
+    int rc__ = (expr);    \
+    if (rc__) return rc__; \
+  } while (0)
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CU(cudaMalloc(&p, want));
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// ---- row classification -------------------------------------------------------------
+constexpr int kDualBins = 6;  // MT_MAX = 4, 8, 12, 16, 20, 24  (n <= 16 .. 96)
+
+struct WorkPlan {
+  // host-side lists (indices into the row list)
+  std::vector<int32_t> dual[kDualBins];
+  std::vector<int32_t> fused;
+  std::vector<int32_t> multi, multi_first_item, multi_n_items;
+  std::vector<int32_t> item_row, item_off;
+  int64_t ratings_dual[kDualBins] = {0};
+  int64_t ratings_fused = 0, ratings_multi = 0;
+};
+
+void classify(const int32_t* row_len, int n_rows, int dual_max, int split_cols, WorkPlan& w) {
+  for (int r = 0; r < n_rows; ++r) {
+    const int n = row_len[r];
+    if (n <= 0) continue;  // Q2 degenerate row (A = 0 upstream): skipped, see DESIGN.md
+    if (n <= dual_max) {
+      const int b = (n - 1) / 16;
+      w.dual[b].push_back(r);
+      w.ratings_dual[b] += n;
+    } else if (n <= split_cols) {
+      w.fused.push_back(r);
+      w.ratings_fused += n;
+    } else {
+      w.multi.push_back(r);
+      w.multi_first_item.push_back((int32_t)w.item_row.size());
+      int cnt = 0;
+      for (int off = 0; off < n; off += split_cols) {
+        w.item_row.push_back(r);
+        w.item_off.push_back(off);
+        ++cnt;
+      }
+      w.multi_n_items.push_back(cnt);
+      w.ratings_multi += n;
+    }
+  }
+  auto by_len_desc = [&](int32_t a, int32_t b) { return row_len[a] != row_len[b] ? row_len[a] > row_len[b] : a < b; };
+  for (auto& d : w.dual) std::sort(d.begin(), d.end(), by_len_desc);
+  std::sort(w.fused.begin(), w.fused.end(), by_len_desc);
+}
+
+// Device-resident plan: one packed int32 array + offsets
+struct DevPlan {
+  int32_t* base = nullptr;  // not owned when it lives in a staging slot
+  int n_dual[kDualBins] = {0};
+  size_t off_dual[kDualBins] = {0};
+  int n_fused = 0, n_multi = 0, n_items = 0;
+  size_t off_fused = 0, off_multi = 0, off_multi_first = 0, off_multi_n = 0, off_item_row = 0, off_item_off = 0;
+  int64_t ratings_dual[kDualBins] = {0};
+  int64_t ratings_fused = 0, ratings_multi = 0;
+  size_t words = 0;
+};
+
+size_t plan_words(const WorkPlan& w) {
+  size_t n = 0;
+  for (auto& d : w.dual) n += d.size();
+  n += w.fused.size() + 3 * w.multi.size() + 2 * w.item_row.size();
+  return n;
+}
+
+void pack_plan(const WorkPlan& w, int32_t* host, DevPlan& p) {
+  size_t o = 0;
+  auto put = [&](const std::vector<int32_t>& v, size_t& off) {
+    off = o;
+    if (!v.empty()) memcpy(host + o, v.data(), v.size() * sizeof(int32_t));
+    o += v.size();
+  };
+  for (int b = 0; b < kDualBins; ++b) {
+    put(w.dual[b], p.off_dual[b]);
+    p.n_dual[b] = (int)w.dual[b].size();
+    p.ratings_dual[b] = w.ratings_dual[b];
+  }
+  put(w.fused, p.off_fused);
+  put(w.multi, p.off_multi);
+  put(w.multi_first_item, p.off_multi_first);
+  put(w.multi_n_items, p.off_multi_n);
+  put(w.item_row, p.off_item_row);
+  put(w.item_off, p.off_item_off);
+  p.n_fused = (int)w.fused.size();
+  p.n_multi = (int)w.multi.size();
+  p.n_items = (int)w.item_row.size();
+  p.ratings_fused = w.ratings_fused;
+  p.ratings_multi = w.ratings_multi;
+  p.words = o;
+}
+
+struct RowSet {
+  bool used = false;
+  int step_type = 0;
+  int n_rows = 0;
+  int64_t span = 0, nnz = 0;
+  int n_portions = 0;
+  DevBuf rows;      // row_ids | row_len | portion_first (int32) then row_start (int64), packed
+  DevBuf ratings;   // indx (int32) | vals (float)
+  DevBuf plan;      // DevPlan words
+  DevBuf sums;      // rmse: row_sums [R][2] | portion_sums [P][3]
+  RowsView view{};
+  const int32_t* d_portion_first = nullptr;
+  DevPlan dplan;
+};
+
+struct Slot {  // staging for the per-portion path
+  void* host = nullptr;
+  size_t host_cap = 0;
+  DevBuf dev;
+  cudaEvent_t done = nullptr;
+  bool pending = false;
+};
+constexpr int kSlots = 4;
+
+struct ProfRec {
+  int cls;
+  cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct ycnr_ctx {
+  ycnr_options opts{};
+  int k = 0;
+  int dual_max = 0;
+  int split_cols = 0;
+  cudaStream_t stream = nullptr;
+  float* d_fac[2] = {nullptr, nullptr};
+  float* h_fac[2] = {nullptr, nullptr};
+  bool h_registered[2] = {false, false};
+  bool device_current[2] = {false, false};
+  int64_t fac_rows[2] = {0, 0};
+  std::vector<void*> peers[2];
+  std::vector<RowSet> rowsets;
+  DevBuf partial;      // split-row tile partials
+  DevBuf gather_tmp;   // ycnr_s_als_build_sub_fixed_facts
+  Slot slots[kSlots];
+  int next_slot = 0;
+  // per-portion step state
+  int step_type = -1;
+  double rmse_shift = 0.0;
+  std::vector<std::pair<int32_t, int32_t>> solved_ranges;  // [first,last] row ids per portion
+  // profiling
+  std::vector<ProfRec> prof_open;
+  std::vector<cudaEvent_t> ev_pool;
+  ycnr_profile prof{};
+};
+
+namespace {
+
+int set_device(ycnr_ctx* c) {
+  CU(cudaSetDevice(c->opts.device));
+  return 0;
+}
+
+DstList make_dst(ycnr_ctx* c, int which) {
+  DstList d{};
+  d.p[0] = c->d_fac[which];
+  d.n = 1;
+  for (void* p : c->peers[which])
+    if (d.n < YCNR_MAX_DST) d.p[d.n++] = (float*)p;
+  return d;
+}
+
+struct ProfScope {
+  ycnr_ctx* c;
+  int cls;
+  cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(ycnr_ctx* ctx, int cls_, int64_t rows, int64_t ratings) : c(ctx), cls(cls_) {
+    c->prof.launches[cls]++;
+    c->prof.rows[cls] += rows;
+    c->prof.ratings[cls] += ratings;
+    c->prof.total_launches++;
+    if (!c->opts.profile) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+      else cudaEventCreate(&e);
+      return e;
+    };
+    a = get();
+    b = get();
+    cudaEventRecord(a, c->stream);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, c->stream);
+    c->prof_open.push_back({cls, a, b});
+  }
+};
+
+// ---- kernel dispatch -----------------------------------------------------------------
+template <int KT, int NT>
+int launch_primal_kt(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p, const int32_t* plan_base) {
+  using namespace ycnr;
+  constexpr int NTILES = KT * (KT + 1) / 2 + KT;
+  if (p.n_fused > 0) {
+    PrimalArgs a = base;
+    a.work = plan_base + p.off_fused;
+    ProfScope ps(c, YCNR_K_PRIMAL_FUSED, p.n_fused, p.ratings_fused);
+    als_primal_kernel<KT, NT, 1, MODE_FUSED><<<p.n_fused, NT, 0, c->stream>>>(a);
+  }
+  if (p.n_items > 0) {
+    OK(c->partial.ensure((size_t)p.n_items * NTILES * 16 * sizeof(float)));
+    PrimalArgs a = base;
+    a.item_row = plan_base + p.off_item_row;
+    a.item_off = plan_base + p.off_item_off;
+    a.partial = (float*)c->partial.p;
+    {
+      ProfScope ps(c, YCNR_K_GRAM_PARTIAL, p.n_items, p.ratings_multi);
+      als_primal_kernel<KT, NT, 1, MODE_PARTIAL><<<p.n_items, NT, 0, c->stream>>>(a);
+    }
+    a.work = plan_base + p.off_multi;
+    a.row_first_item = plan_base + p.off_multi_first;
+    a.row_n_items = plan_base + p.off_multi_n;
+    {
+      ProfScope ps(c, YCNR_K_REDUCE_SOLVE, p.n_multi, 0);
+      als_primal_kernel<KT, NT, 1, MODE_REDUCE><<<p.n_multi, NT, 0, c->stream>>>(a);
+    }
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int launch_primal(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p, const int32_t* plan_base) {
+  const int k = c->k;
+  if (k <= 20) return launch_primal_kt<5, 32>(c, base, p, plan_base);
+  if (k <= 32) return launch_primal_kt<8, 64>(c, base, p, plan_base);
+  if (k <= 64) return launch_primal_kt<16, 160>(c, base, p, plan_base);
+  if (k <= 100) return launch_primal_kt<25, 352>(c, base, p, plan_base);
+  if (k <= 128) return launch_primal_kt<32, 576>(c, base, p, plan_base);
+  return fail("factorsCount %d > 128 is not supported by this build", k);
+}
+
+template <int MT_MAX, int NT>
+int launch_dual_bin(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t ratings, const int32_t* work) {
+  using namespace ycnr;
+  if (count <= 0) return 0;
+  DualArgs a = base;
+  a.work = work;
+  const size_t smem = ((size_t)4 * MT_MAX * a.pitch + (MT_MAX + 1) * 16 + 16 + 8 * MT_MAX) * sizeof(float);
+  static size_t configured = 0;  // per instantiation
+  if (smem > 48 * 1024 && smem > configured) {
+    CU(cudaFuncSetAttribute(als_dual_kernel<MT_MAX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  ProfScope ps(c, YCNR_K_DUAL_FUSED, count, ratings);
+  als_dual_kernel<MT_MAX, NT><<<count, NT, smem, c->stream>>>(a);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int dual_pitch(int k) {
+  int p = (k + 3) & ~3;
+  if (((p >> 2) & 1) == 0) p += 4;
+  return p;
+}
+
+// One ALS half-step over a device-resident row list + plan.
+int run_als(ycnr_ctx* c, int step_type, const RowsView& view, const DevPlan& p, const int32_t* plan_base) {
+  const int solved = step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
+  const int fixed = 1 - solved;
+  const double lambda = step_type == YCNR_BY_USER ? c->opts.user_fact_reg : c->opts.item_fact_reg;
+  ycnr::DualArgs d{};
+  d.rows = view;
+  d.fixed = c->d_fac[fixed];
+  d.k = c->k;
+  d.pitch = dual_pitch(c->k);
+  d.lambda = lambda;
+  d.dst = make_dst(c, solved);
+  OK((launch_dual_bin<4, 32>(c, d, p.n_dual[0], p.ratings_dual[0], plan_base + p.off_dual[0])));
+  OK((launch_dual_bin<8, 64>(c, d, p.n_dual[1], p.ratings_dual[1], plan_base + p.off_dual[1])));
+  OK((launch_dual_bin<12, 96>(c, d, p.n_dual[2], p.ratings_dual[2], plan_base + p.off_dual[2])));
+  OK((launch_dual_bin<16, 160>(c, d, p.n_dual[3], p.ratings_dual[3], plan_base + p.off_dual[3])));
+  OK((launch_dual_bin<20, 256>(c, d, p.n_dual[4], p.ratings_dual[4], plan_base + p.off_dual[4])));
+  OK((launch_dual_bin<24, 352>(c, d, p.n_dual[5], p.ratings_dual[5], plan_base + p.off_dual[5])));
+  ycnr::PrimalArgs a{};
+  a.rows = view;
+  a.fixed = c->d_fac[fixed];
+  a.k = c->k;
+  a.lambda = lambda;
+  a.dst = d.dst;
+  a.split_cols = c->split_cols;
+  OK(launch_primal(c, a, p, plan_base));
+  c->device_current[solved] = true;
+  return 0;
+}
+
+int run_rmse(ycnr_ctx* c, const RowsView& view, int n_rows, int64_t nnz, double shift, double* d_row_sums,
+             const int32_t* d_portion_first, int n_portions, double* d_portion_sums) {
+  if (n_rows <= 0 || n_portions <= 0) return 0;
+  ycnr::RmseArgs a{};
+  a.rows = view;
+  a.U = c->d_fac[YCNR_USER_FACTORS];
+  a.V = c->d_fac[YCNR_ITEM_FACTORS];
+  a.k = c->k;
+  a.n_rows = n_rows;
+  a.shift = shift;
+  a.row_sums = d_row_sums;
+  {
+    ProfScope ps(c, YCNR_K_RMSE_ROWS, n_rows, nnz);
+    const int warps_per_cta = 8;
+    ycnr::rmse_rows_kernel<<<(n_rows + warps_per_cta - 1) / warps_per_cta, 256, 0, c->stream>>>(a);
+  }
+  {
+    ProfScope ps(c, YCNR_K_RMSE_REDUCE, n_portions, 0);
+    ycnr::rmse_portion_reduce_kernel<<<n_portions, 256, 0, c->stream>>>(d_row_sums, view.row_len, d_portion_first,
+                                                                         d_portion_sums);
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int ensure_fixed_current(ycnr_ctx* c, int which) {
+  if (c->device_current[which]) return 0;
+  if (!c->h_fac[which]) return fail("factor matrix %d has no host copy attached and no device content", which);
+  CU(cudaMemcpyAsync(c->d_fac[which], c->h_fac[which], (size_t)c->fac_rows[which] * c->k * sizeof(float),
+                     cudaMemcpyHostToDevice, c->stream));
+  c->device_current[which] = true;
+  return 0;
+}
+
+// Parse a portion header (EmfWorker.js:176-219) and stage header + plan + ratings in one slot.
+struct StagedPortion {
+  RowsView view{};
+  DevPlan plan;
+  const int32_t* plan_base = nullptr;
+  int n_rows = 0;
+  int64_t ratings = 0;
+  int32_t first_row = -1, last_row = -1;
+  double* d_sums = nullptr;        // rmse scratch: row_sums[R][2] | portion_sums[3]
+  const int32_t* d_pfirst = nullptr;
+  Slot* slot = nullptr;
+};
+
+int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals, bool with_plan,
+                  StagedPortion& s) {
+  const int R = rows[0];
+  if (R < 0) return fail("portion header: negative row count");
+  s.n_rows = R;
+  std::vector<int32_t> ids(R), len(R);
+  std::vector<int64_t> start(R);
+  int64_t off = 0;
+  for (int r = 0; r < R; ++r) {
+    ids[r] = rows[1 + 2 * r];
+    len[r] = rows[1 + 2 * r + 1];
+    if (len[r] < 0) return fail("portion header: negative cols");
+    start[r] = off;
+    off += len[r];
+  }
+  s.ratings = off;
+  if (R > 0) { s.first_row = ids[0]; s.last_row = ids[R - 1]; }
+  WorkPlan w;
+  if (with_plan) classify(len.data(), R, c->dual_max, c->split_cols, w);
+  const size_t pw = with_plan ? plan_words(w) : 0;
+  // layout (8-byte aligned sections): start[R] i64 | sums f64 [2R+3] | ids[R] | len[R] | pfirst[2] | plan | indx | vals
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  size_t o_start = 0;
+  size_t o_sums = al(o_start + (size_t)R * 8);
+  size_t o_ids = al(o_sums + (size_t)(2 * R + 3) * 8);
+  size_t o_len = al(o_ids + (size_t)R * 4);
+  size_t o_pf = al(o_len + (size_t)R * 4);
+  size_t o_plan = al(o_pf + 8);
+  size_t o_indx = al(o_plan + pw * 4);
+  size_t o_vals = al(o_indx + (size_t)off * 4);
+  size_t total = al(o_vals + (size_t)off * 4);
+
+  Slot& sl = c->slots[c->next_slot];
+  c->next_slot = (c->next_slot + 1) % kSlots;
+  if (sl.pending) {
+    CU(cudaEventSynchronize(sl.done));
+    sl.pending = false;
+  }
+  if (!sl.done) CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  if (total > sl.host_cap) {
+    if (sl.host) cudaFreeHost(sl.host);
+    sl.host = nullptr;
+    sl.host_cap = 0;
+    size_t want = total + total / 4 + 4096;
+    CU(cudaMallocHost(&sl.host, want));
+    sl.host_cap = want;
+  }
+  OK(sl.dev.ensure(total));
+  char* h = (char*)sl.host;
+  if (R) {
+    memcpy(h + o_start, start.data(), (size_t)R * 8);
+    memcpy(h + o_ids, ids.data(), (size_t)R * 4);
+    memcpy(h + o_len, len.data(), (size_t)R * 4);
+  }
+  int32_t pf[2] = {0, R};
+  memcpy(h + o_pf, pf, 8);
+  if (with_plan) pack_plan(w, (int32_t*)(h + o_plan), s.plan);
+  if (off) {
+    memcpy(h + o_indx, indx, (size_t)off * 4);
+    memcpy(h + o_vals, vals, (size_t)off * 4);
+  }
+  char* d = (char*)sl.dev.p;
+  // the f64 scratch section is not uploaded, but it sits inside the contiguous range
+  CU(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, c->stream));
+  s.view.row_start = (const int64_t*)(d + o_start);
+  s.view.row_ids = (const int32_t*)(d + o_ids);
+  s.view.row_len = (const int32_t*)(d + o_len);
+  s.view.indx = (const int32_t*)(d + o_indx);
+  s.view.vals = (const float*)(d + o_vals);
+  s.d_sums = (double*)(d + o_sums);
+  s.d_pfirst = (const int32_t*)(d + o_pf);
+  s.plan_base = (const int32_t*)(d + o_plan);
+  s.slot = &sl;
+  return 0;
+}
+
+int finish_slot(ycnr_ctx* c, Slot* sl) {
+  CU(cudaEventRecord(sl->done, c->stream));
+  sl->pending = true;
+  return 0;
+}
+
+void collect_profile(ycnr_ctx* c) {
+  for (auto& r : c->prof_open) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) c->prof.ms[r.cls] += ms;
+    c->ev_pool.push_back(r.a);
+    c->ev_pool.push_back(r.b);
+  }
+  c->prof_open.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ycnr_last_error(void) { return g_err; }
+
+int ycnr_device_count(int32_t* count_out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count_out = 0;
+    return fail("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  *count_out = n;
+  return 0;
+}
+
+int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
+  if (!o || !out) return fail("ycnr_create: null argument");
+  *out = nullptr;
+  if (o->use_double_precision)
+    return fail("useDoublePrecision=true is not supported: the B200 path computes in float32 only (EmfBase.js:112)");
+  if (o->lowmem) return fail("lowmem=true (file-backed factors, EmfBase.js:116) is not supported by the GPU path");
+  if (o->factors_count <= 0 || o->factors_count > 128)
+    return fail("factorsCount %d outside the supported range 1..128", o->factors_count);
+  if (o->total_users <= 0 || o->total_items <= 0) return fail("totalUsersCount/totalItemsCount must be positive");
+  if (o->gram_path == YCNR_GRAM_TC3XTF32) return fail("gram_path=TC3XTF32 is not available in this build");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return fail("no CUDA device available (%s): the ALS hot path has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (o->device < 0 || o->device >= ndev) return fail("device %d out of range (0..%d)", o->device, ndev - 1);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, o->device));
+  if (prop.major != 10)
+    return fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only", o->device, prop.major, prop.minor);
+  ycnr_ctx* c = new ycnr_ctx();
+  c->opts = *o;
+  c->k = o->factors_count;
+  const int dflt_dual = std::min(96, std::max(0, ((c->k - 1) / 4) * 4));
+  c->dual_max = o->dual_max_cols < 0 ? dflt_dual : std::min(96, o->dual_max_cols);
+  c->split_cols = o->split_cols > 0 ? std::max(o->split_cols, ycnr::kStageRows) : 4096;
+  if (c->dual_max > c->split_cols) c->dual_max = c->split_cols;
+  c->fac_rows[0] = o->total_users;
+  c->fac_rows[1] = o->total_items;
+  CU(cudaSetDevice(o->device));
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int w = 0; w < 2; ++w) CU(cudaMalloc(&c->d_fac[w], (size_t)c->fac_rows[w] * c->k * sizeof(float)));
+  *out = c;
+  return 0;
+}
+
+int ycnr_destroy(ycnr_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->opts.device);
+  cudaStreamSynchronize(c->stream);
+  collect_profile(c);
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  for (int w = 0; w < 2; ++w) {
+    if (c->h_registered[w]) cudaHostUnregister(c->h_fac[w]);
+    if (c->d_fac[w]) cudaFree(c->d_fac[w]);
+  }
+  for (auto& rs : c->rowsets) { rs.rows.release(); rs.ratings.release(); rs.plan.release(); rs.sums.release(); }
+  for (auto& s : c->slots) {
+    if (s.host) cudaFreeHost(s.host);
+    s.dev.release();
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  c->partial.release();
+  c->gather_tmp.release();
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+// ---- factor store ---------------------------------------------------------------------
+int ycnr_attach_factors(ycnr_ctx* c, float* uf, float* vf) {
+  if (!c || !uf || !vf) return fail("ycnr_attach_factors: null argument");
+  OK(set_device(c));
+  float* hp[2] = {uf, vf};
+  for (int w = 0; w < 2; ++w) {
+    if (c->h_registered[w]) { cudaHostUnregister(c->h_fac[w]); c->h_registered[w] = false; }
+    c->h_fac[w] = hp[w];
+    const size_t bytes = (size_t)c->fac_rows[w] * c->k * sizeof(float);
+    // page-lock the shm segment so the per-step copies are true DMA; pageable still works
+    if (cudaHostRegister(hp[w], bytes, cudaHostRegisterDefault) == cudaSuccess) c->h_registered[w] = true;
+    else cudaGetLastError();
+    c->device_current[w] = false;
+    OK(ensure_fixed_current(c, w));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ycnr_upload_factors(ycnr_ctx* c, int32_t which) {
+  if (!c || which < 0 || which > 1) return fail("ycnr_upload_factors: bad argument");
+  OK(set_device(c));
+  c->device_current[which] = false;
+  OK(ensure_fixed_current(c, which));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ycnr_download_factors(ycnr_ctx* c, int32_t which, int32_t row_from, int32_t row_cnt) {
+  if (!c || which < 0 || which > 1) return fail("ycnr_download_factors: bad argument");
+  if (!c->h_fac[which]) return fail("ycnr_download_factors: no host matrix attached");
+  if (row_cnt < 0) { row_from = 0; row_cnt = (int32_t)c->fac_rows[which]; }
+  if (row_from < 0 || (int64_t)row_from + row_cnt > c->fac_rows[which]) return fail("ycnr_download_factors: row range");
+  OK(set_device(c));
+  const size_t off = (size_t)row_from * c->k;
+  CU(cudaMemcpyAsync(c->h_fac[which] + off, c->d_fac[which] + off, (size_t)row_cnt * c->k * sizeof(float),
+                     cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ycnr_invalidate_device(ycnr_ctx* c, int32_t which) {
+  if (!c || which < 0 || which > 1) return fail("ycnr_invalidate_device: bad argument");
+  c->device_current[which] = false;
+  return 0;
+}
+
+int ycnr_device_factors(ycnr_ctx* c, int32_t which, void** out) {
+  if (!c || which < 0 || which > 1 || !out) return fail("ycnr_device_factors: bad argument");
+  *out = c->d_fac[which];
+  return 0;
+}
+
+int ycnr_stream(ycnr_ctx* c, void** out) {
+  if (!c || !out) return fail("ycnr_stream: bad argument");
+  *out = (void*)c->stream;
+  return 0;
+}
+
+int ycnr_synchronize(ycnr_ctx* c) {
+  if (!c) return fail("ycnr_synchronize: null context");
+  OK(set_device(c));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- per-portion path -----------------------------------------------------------------
+int ycnr_start_train_step(ycnr_ctx* c, int32_t step_type) {
+  if (!c || (step_type != YCNR_BY_USER && step_type != YCNR_BY_ITEM)) return fail("ycnr_start_train_step: bad stepType");
+  OK(set_device(c));
+  c->step_type = step_type;
+  c->solved_ranges.clear();
+  const int solved = step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
+  OK(ensure_fixed_current(c, 1 - solved));
+  OK(ensure_fixed_current(c, solved));  // rows that are not solved keep their values
+  return 0;
+}
+
+int ycnr_als_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals,
+                     ycnr_portion_info* info) {
+  if (!c || !rows || !indx || !vals) return fail("ycnr_als_portion: null argument");
+  if (c->step_type != YCNR_BY_USER && c->step_type != YCNR_BY_ITEM)
+    return fail("ycnr_als_portion: call ycnr_start_train_step first");
+  const double t0 = now_ms();
+  OK(set_device(c));
+  StagedPortion s;
+  OK(stage_portion(c, rows, indx, vals, true, s));
+  if (s.n_rows > 0) {
+    OK(run_als(c, c->step_type, s.view, s.plan, s.plan_base));
+    c->solved_ranges.emplace_back(s.first_row, s.last_row);
+  }
+  OK(finish_slot(c, s.slot));
+  if (info) {
+    memset(info, 0, sizeof(*info));
+    info->rows_from = s.first_row;
+    info->rows_cnt = s.n_rows;
+    info->ratings_in_portion = s.ratings;
+    info->time_ms = now_ms() - t0;
+  }
+  return 0;
+}
+
+int ycnr_end_train_step(ycnr_ctx* c) {
+  if (!c) return fail("ycnr_end_train_step: null context");
+  if (c->step_type != YCNR_BY_USER && c->step_type != YCNR_BY_ITEM) return fail("ycnr_end_train_step: no step open");
+  OK(set_device(c));
+  const int solved = c->step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
+  if (c->h_fac[solved]) {
+    // merge the per-portion [first,last] ranges (ascending in practice) and copy them back
+    auto& v = c->solved_ranges;
+    std::sort(v.begin(), v.end());
+    size_t i = 0;
+    while (i < v.size()) {
+      int32_t lo = v[i].first, hi = v[i].second;
+      size_t j = i + 1;
+      while (j < v.size() && v[j].first <= hi + 1) { hi = std::max(hi, v[j].second); ++j; }
+      const size_t off = (size_t)lo * c->k;
+      CU(cudaMemcpyAsync(c->h_fac[solved] + off, c->d_fac[solved] + off, (size_t)(hi - lo + 1) * c->k * sizeof(float),
+                         cudaMemcpyDeviceToHost, c->stream));
+      i = j;
+    }
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  c->solved_ranges.clear();
+  c->step_type = -1;
+  return 0;
+}
+
+int ycnr_start_calc_rmse(ycnr_ctx* c, int32_t step_type, double shift) {
+  if (!c || (step_type != YCNR_RMSE_VALIDATE && step_type != YCNR_RMSE_TEST)) return fail("ycnr_start_calc_rmse: bad stepType");
+  OK(set_device(c));
+  c->step_type = step_type;
+  c->rmse_shift = shift;
+  OK(ensure_fixed_current(c, YCNR_USER_FACTORS));
+  OK(ensure_fixed_current(c, YCNR_ITEM_FACTORS));
+  return 0;
+}
+
+int ycnr_rmse_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals,
+                      ycnr_portion_info* info) {
+  if (!c || !rows || !indx || !vals || !info) return fail("ycnr_rmse_portion: null argument");
+  if (c->step_type != YCNR_RMSE_VALIDATE && c->step_type != YCNR_RMSE_TEST)
+    return fail("ycnr_rmse_portion: call ycnr_start_calc_rmse first");
+  const double t0 = now_ms();
+  OK(set_device(c));
+  StagedPortion s;
+  OK(stage_portion(c, rows, indx, vals, false, s));
+  double sums[3] = {0, 0, 0};
+  if (s.n_rows > 0) {
+    double* d_portion = s.d_sums + 2 * (size_t)s.n_rows;
+    OK(run_rmse(c, s.view, s.n_rows, s.ratings, c->rmse_shift, s.d_sums, s.d_pfirst, 1, d_portion));
+    CU(cudaMemcpyAsync(sums, d_portion, sizeof(sums), cudaMemcpyDeviceToHost, c->stream));
+  }
+  OK(finish_slot(c, s.slot));
+  CU(cudaStreamSynchronize(c->stream));
+  memset(info, 0, sizeof(*info));
+  info->rows_from = s.first_row;
+  info->rows_cnt = s.n_rows;
+  info->ratings_in_portion = s.ratings;
+  info->r_sum_diff2 = sums[0];
+  info->r_cnt = sums[1];
+  info->r_sum = sums[2];
+  info->time_ms = now_ms() - t0;
+  return 0;
+}
+
+int ycnr_s_als_build_sub_fixed_facts(ycnr_ctx* c, float* sub, const float* fixed, int64_t fixed_rows,
+                                     const int32_t* indx, int32_t cols, int32_t k) {
+  if (!c || !sub || !fixed || !indx || cols < 0 || k <= 0) return fail("ycnr_s_als_build_sub_fixed_facts: bad argument");
+  if (cols == 0) return 0;
+  for (int i = 0; i < cols; ++i)
+    if (indx[i] < 0 || indx[i] >= fixed_rows) return fail("ycnr_s_als_build_sub_fixed_facts: index %d out of range", indx[i]);
+  OK(set_device(c));
+  const size_t fb = (size_t)fixed_rows * k * sizeof(float), sb = (size_t)cols * k * sizeof(float);
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  OK(c->gather_tmp.ensure(al(fb) + al(sb) + al((size_t)cols * sizeof(int32_t))));
+  char* d = (char*)c->gather_tmp.p;
+  float* d_fixed = (float*)d;
+  float* d_sub = (float*)(d + al(fb));
+  int32_t* d_idx = (int32_t*)(d + al(fb) + al(sb));
+  CU(cudaMemcpyAsync(d_fixed, fixed, fb, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_idx, indx, (size_t)cols * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, YCNR_K_GATHER, cols, cols);
+    const int64_t total = (int64_t)cols * k;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+    ycnr::gather_rows_kernel<<<grid, 256, 0, c->stream>>>(d_sub, d_fixed, d_idx, cols, k);
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(sub, d_sub, sb, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- bulk path --------------------------------------------------------------------------
+int ycnr_rowset_create(ycnr_ctx* c, int32_t step_type, int32_t n_rows, const int32_t* row_ids,
+                       const int64_t* row_start, const int32_t* row_len, const int32_t* indx,
+                       const float* vals, int64_t span, const int32_t* portion_first, int32_t n_portions,
+                       int32_t* out) {
+  if (!c || !out || n_rows < 0 || span < 0) return fail("ycnr_rowset_create: bad argument");
+  if (step_type < YCNR_BY_USER || step_type > YCNR_RMSE_TEST) return fail("ycnr_rowset_create: bad stepType");
+  if (n_rows && (!row_ids || !row_start || !row_len)) return fail("ycnr_rowset_create: null row arrays");
+  if (span && (!indx || !vals)) return fail("ycnr_rowset_create: null ratings arrays");
+  OK(set_device(c));
+  const int64_t lim_cols = (step_type == YCNR_BY_ITEM) ? c->fac_rows[0] : c->fac_rows[1];
+  const int64_t lim_rows = (step_type == YCNR_BY_ITEM) ? c->fac_rows[1] : c->fac_rows[0];
+  int64_t nnz = 0;
+  for (int r = 0; r < n_rows; ++r) {
+    if (row_ids[r] < 0 || row_ids[r] >= lim_rows) return fail("ycnr_rowset_create: row id %d out of range", row_ids[r]);
+    if (row_len[r] < 0 || row_start[r] < 0 || row_start[r] + row_len[r] > span)
+      return fail("ycnr_rowset_create: row %d addresses ratings outside [0, span)", r);
+    nnz += row_len[r];
+  }
+  for (int64_t e = 0; e < span; ++e)
+    if (indx[e] < 0 || indx[e] >= lim_cols) return fail("ycnr_rowset_create: column id %d out of range", indx[e]);
+  int id = -1;
+  for (size_t i = 0; i < c->rowsets.size(); ++i)
+    if (!c->rowsets[i].used) { id = (int)i; break; }
+  if (id < 0) { c->rowsets.emplace_back(); id = (int)c->rowsets.size() - 1; }
+  RowSet& rs = c->rowsets[id];
+  rs = RowSet();
+  rs.used = true;
+  rs.step_type = step_type;
+  rs.n_rows = n_rows;
+  rs.span = span;
+  rs.nnz = nnz;
+  const bool rmse = step_type >= YCNR_RMSE_VALIDATE;
+  int32_t pf_default[2] = {0, n_rows};
+  if (!portion_first || n_portions <= 0) { portion_first = pf_default; n_portions = 1; }
+  rs.n_portions = n_portions;
+  // rows buffer: start[R] i64 | ids[R] | len[R] | pfirst[P+1]
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t o_ids = al((size_t)n_rows * 8), o_len = al(o_ids + (size_t)n_rows * 4), o_pf = al(o_len + (size_t)n_rows * 4);
+  const size_t rows_bytes = al(o_pf + (size_t)(n_portions + 1) * 4);
+  OK(rs.rows.ensure(rows_bytes));
+  char* d = (char*)rs.rows.p;
+  if (n_rows) {
+    CU(cudaMemcpyAsync(d, row_start, (size_t)n_rows * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + o_ids, row_ids, (size_t)n_rows * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + o_len, row_len, (size_t)n_rows * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaMemcpyAsync(d + o_pf, portion_first, (size_t)(n_portions + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  const size_t o_vals = al((size_t)span * 4);
+  OK(rs.ratings.ensure(o_vals + al((size_t)span * 4)));
+  char* dr = (char*)rs.ratings.p;
+  if (span) {
+    CU(cudaMemcpyAsync(dr, indx, (size_t)span * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dr + o_vals, vals, (size_t)span * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  rs.view.row_start = (const int64_t*)d;
+  rs.view.row_ids = (const int32_t*)(d + o_ids);
+  rs.view.row_len = (const int32_t*)(d + o_len);
+  rs.d_portion_first = (const int32_t*)(d + o_pf);
+  rs.view.indx = (const int32_t*)dr;
+  rs.view.vals = (const float*)(dr + o_vals);
+  std::vector<int32_t> packed;
+  if (!rmse) {
+    WorkPlan w;
+    classify(row_len, n_rows, c->dual_max, c->split_cols, w);
+    packed.resize(plan_words(w) + 1);
+    pack_plan(w, packed.data(), rs.dplan);
+    OK(rs.plan.ensure(packed.size() * 4));
+    CU(cudaMemcpyAsync(rs.plan.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    OK(rs.sums.ensure(((size_t)2 * n_rows + 3 * (size_t)n_portions + 4) * sizeof(double)));
+  }
+  CU(cudaStreamSynchronize(c->stream));  // host sources may be freed by the caller on return
+  *out = id;
+  return 0;
+}
+
+int ycnr_rowset_destroy(ycnr_ctx* c, int32_t id) {
+  if (!c || id < 0 || id >= (int)c->rowsets.size() || !c->rowsets[id].used) return fail("ycnr_rowset_destroy: bad id");
+  OK(set_device(c));
+  CU(cudaStreamSynchronize(c->stream));
+  RowSet& rs = c->rowsets[id];
+  rs.rows.release(); rs.ratings.release(); rs.plan.release(); rs.sums.release();
+  rs.used = false;
+  return 0;
+}
+
+int ycnr_als_rowset(ycnr_ctx* c, int32_t id) {
+  if (!c || id < 0 || id >= (int)c->rowsets.size() || !c->rowsets[id].used) return fail("ycnr_als_rowset: bad id");
+  RowSet& rs = c->rowsets[id];
+  if (rs.step_type != YCNR_BY_USER && rs.step_type != YCNR_BY_ITEM) return fail("ycnr_als_rowset: row set is an RMSE set");
+  OK(set_device(c));
+  const int solved = rs.step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
+  OK(ensure_fixed_current(c, 1 - solved));
+  OK(ensure_fixed_current(c, solved));
+  if (rs.n_rows == 0) return 0;
+  return run_als(c, rs.step_type, rs.view, rs.dplan, (const int32_t*)rs.plan.p);
+}
+
+int ycnr_rmse_rowset(ycnr_ctx* c, int32_t id, double shift, double* totals, double* portion_sums) {
+  if (!c || !totals || id < 0 || id >= (int)c->rowsets.size() || !c->rowsets[id].used) return fail("ycnr_rmse_rowset: bad argument");
+  RowSet& rs = c->rowsets[id];
+  if (rs.step_type != YCNR_RMSE_VALIDATE && rs.step_type != YCNR_RMSE_TEST) return fail("ycnr_rmse_rowset: row set is an ALS set");
+  OK(set_device(c));
+  OK(ensure_fixed_current(c, YCNR_USER_FACTORS));
+  OK(ensure_fixed_current(c, YCNR_ITEM_FACTORS));
+  totals[0] = totals[1] = totals[2] = 0.0;
+  if (rs.n_rows == 0) {
+    if (portion_sums) memset(portion_sums, 0, sizeof(double) * 3 * rs.n_portions);
+    return 0;
+  }
+  double* d_rows = (double*)rs.sums.p;
+  double* d_port = d_rows + 2 * (size_t)rs.n_rows;
+  OK(run_rmse(c, rs.view, rs.n_rows, rs.nnz, shift, d_rows, rs.d_portion_first, rs.n_portions, d_port));
+  std::vector<double> tmp;
+  double* hp = portion_sums;
+  if (!hp) { tmp.resize((size_t)3 * rs.n_portions); hp = tmp.data(); }
+  CU(cudaMemcpyAsync(hp, d_port, sizeof(double) * 3 * rs.n_portions, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int p = 0; p < rs.n_portions; ++p) {  // EmfMaster.m_completedPortion 770-774, portion order
+    totals[0] += hp[3 * p];
+    totals[1] += hp[3 * p + 1];
+    totals[2] += hp[3 * p + 2];
+  }
+  return 0;
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------
+int ycnr_ipc_export(ycnr_ctx* c, int32_t which, uint8_t handle_out[64]) {
+  if (!c || which < 0 || which > 1 || !handle_out) return fail("ycnr_ipc_export: bad argument");
+  OK(set_device(c));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, c->d_fac[which]));
+  memcpy(handle_out, &h, 64);
+  return 0;
+}
+
+int ycnr_ipc_import(ycnr_ctx* c, const uint8_t handle[64], void** out) {
+  if (!c || !handle || !out) return fail("ycnr_ipc_import: bad argument");
+  OK(set_device(c));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CU(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int ycnr_ipc_close(ycnr_ctx* c, void* p) {
+  if (!c || !p) return fail("ycnr_ipc_close: bad argument");
+  OK(set_device(c));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaIpcCloseMemHandle(p));
+  return 0;
+}
+
+int ycnr_set_peers(ycnr_ctx* c, int32_t which, int32_t n, void* const* ptrs) {
+  if (!c || which < 0 || which > 1 || n < 0 || n > YCNR_MAX_DST - 1 || (n && !ptrs)) return fail("ycnr_set_peers: bad argument");
+  OK(set_device(c));
+  CU(cudaStreamSynchronize(c->stream));
+  c->peers[which].assign(ptrs, ptrs + n);
+  return 0;
+}
+
+// ---- measurement -----------------------------------------------------------------------------
+int ycnr_profile_reset(ycnr_ctx* c) {
+  if (!c) return fail("ycnr_profile_reset: null context");
+  OK(set_device(c));
+  CU(cudaStreamSynchronize(c->stream));
+  collect_profile(c);
+  memset(&c->prof, 0, sizeof(c->prof));
+  return 0;
+}
+
+int ycnr_profile_read(ycnr_ctx* c, ycnr_profile* out) {
+  if (!c || !out) return fail("ycnr_profile_read: bad argument");
+  OK(set_device(c));
+  CU(cudaStreamSynchronize(c->stream));
+  collect_profile(c);
+  *out = c->prof;
+  return 0;
+}
+
+}  // extern "C"

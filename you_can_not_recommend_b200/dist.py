@@ -1,0 +1,134 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch).
+
+The reference clusters over TCP: every node holds full replicas of U and V, solved row
+ranges are streamed to all peers ('alsSaveCalcedFactors', EmfMaster.js:711-723) and RMSE
+partial sums are reduced on the lord ('rmseSaveCalcs', EmfMaster.js:726-736).  Here:
+
+  * portions are split into contiguous nnz-balanced slices per rank (balanced_cuts),
+  * after a half-step every rank broadcasts its solved row range of the replica
+    (broadcast_ranges: an all-gather with unequal counts), or — fused variant — the solve
+    kernels store rows straight into peer replicas (connect_peers + barrier),
+  * RMSE sums are combined in rank order, the last portion's partials travel with them (Q7).
+
+The same functions run on CPU tensors with the gloo backend (tests/test_dist_gloo.py).
+"""
+import os
+
+import numpy as np
+
+
+def balanced_cuts(ends, world):
+    """ends[p] = cumulative ratings up to and including portion p (non-decreasing).
+    Returns cuts[world+1] (portion indices) so that rank r takes [cuts[r], cuts[r+1])."""
+    ends = np.asarray(ends, np.int64)
+    n = len(ends)
+    cuts = np.zeros(world + 1, np.int64)
+    cuts[world] = n
+    total = int(ends[-1]) if n else 0
+    for g in range(1, world):
+        target = (total * g) // world
+        c = int(np.searchsorted(ends, target, side="left")) + 1 if total else 0
+        # choose the boundary closer to the target
+        if c - 1 >= 1 and abs(int(ends[c - 2]) - target) <= abs(int(ends[min(c, n) - 1]) - target):
+            c -= 1
+        cuts[g] = min(max(c, cuts[g - 1]), n)
+    return cuts
+
+
+def init_from_env(backend=None):
+    """torchrun contract: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+def all_ranges(my_range, world, group=None):
+    """Every rank's solved row-id range [a, b)."""
+    if world == 1:
+        return [tuple(my_range)]
+    import torch.distributed as dist
+    out = [None] * world
+    dist.all_gather_object(out, tuple(int(x) for x in my_range), group=group)
+    return out
+
+
+def broadcast_ranges(mat, ranges, group=None):
+    """mat: 2-D torch tensor replica (rows x k) on every rank; rank r owns rows ranges[r].
+    All-gather with unequal counts = one broadcast per non-empty range, issued together."""
+    import torch.distributed as dist
+    works = []
+    for r, (a, b) in enumerate(ranges):
+        if b > a:
+            works.append(dist.broadcast(mat[a:b], src=r, group=group, async_op=True))
+    for w in works:
+        w.wait()
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of a raw device pointer (no ownership)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def device_tensor(ctx, which, rows, k, device):
+    import torch
+    return torch.as_tensor(_DevArray(ctx.device_factors_ptr(which), (rows, k)), device=torch.device("cuda", device))
+
+
+def refresh_replicas(ctx, which, k, ranges, rank, group=None, host=None):
+    """After a half-step: make replica `which` identical on all ranks."""
+    import torch
+    rows = ctx.total_users if which == 0 else ctx.total_items
+    ctx.synchronize()                                  # library stream -> done
+    dev = torch.cuda.current_device()
+    t = device_tensor(ctx, which, rows, k, dev)
+    broadcast_ranges(t, ranges, group)
+    torch.cuda.synchronize()
+    if host is not None:                               # per-portion mode: host segment is the truth
+        for r, (a, b) in enumerate(ranges):
+            if r != rank and b > a:
+                ctx.download_factors(which, a, b - a)
+
+
+def connect_peers(ctx, which, rank, world, group=None):
+    """Fused all-gather: exchange CUDA IPC handles of replica `which` and register the peers,
+    so the solve kernels store each solved row into every replica (NVLink peer stores)."""
+    import torch.distributed as dist
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.ipc_export(which), group=group)
+    ptrs = [ctx.ipc_import(h) for r, h in enumerate(handles) if r != rank]
+    ctx.set_peers(which, ptrs)
+    return ptrs
+
+
+def reduce_rmse(sums, last, group=None):
+    """Combine (rSumDiff2, rCnt, rSum) over ranks in rank order; `last` = partials of the globally
+    last portion = the highest rank that had any portion."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = [None] * world
+    dist.all_gather_object(out, (tuple(float(x) for x in sums),
+                                 None if last is None else {"rSum": float(last["rSum"]), "rCnt": float(last["rCnt"])}),
+                           group=group)
+    tot = [0.0, 0.0, 0.0]
+    glast = None
+    for s, l in out:
+        for i in range(3):
+            tot[i] += s[i]
+        if l is not None:
+            glast = l
+    return tuple(tot), glast

@@ -1,0 +1,285 @@
+"""EmfMaster — single-box driver of the worker interface (the caller of the hot path).
+
+This is the minimum of lib/emf/EmfMaster.js + lib/emf/EmfLord.js needed to drive the
+workers exactly as the reference does, with the PostgreSQL side replaced by an
+in-memory RatingsTable (front_end.py):
+
+  prepareToTrain ........ EmfLord.js:617-653, 39-43 (split to sets, stats, portions),
+                          EmfMaster.js:138-142,156-234 (worker + portion buffers)
+  alsTrainStep .......... EmfLord.js:963-984, EmfMaster.js:364-383,645-689
+  calcRmse .............. EmfLord.js:1043-1081, EmfMaster.js:389-412,757-786 (Q7)
+  train ................. EmfLord.js:892-902 (Q8 order)
+
+Two ways to run a step: the drop-in per-portion messages (reference wire format), or
+`bulk` row sets that keep every portion of a step resident on the GPU.
+With world > 1 (one process per GPU, torch.distributed) portions are split into
+contiguous nnz-balanced slices per rank and the solved slices are exchanged after every
+half-step (dist.py), replacing 'alsSaveCalcedFactors' (EmfMaster.js:711-723).
+"""
+import math
+
+import numpy as np
+
+from . import dist as ydist
+from . import front_end as fe
+from . import native
+from .emf_base import EmfBase
+from .emf_worker import EmfProcess, EmfWorker
+
+STEP_MASK = {"byUser": fe.MASK_TRAIN, "byItem": fe.MASK_TRAIN,
+             "rmseValidate": fe.MASK_VALIDATE, "rmseTest": fe.MASK_TEST}
+
+
+class EmfMaster(EmfBase):
+    def __init__(self, table, options=None, rank=0, world=1, group=None):
+        super().__init__(options)
+        self.table = table
+        self.rank, self.world, self.group = rank, world, group
+        self.portionsRowIdTo = {}
+        self.portionsCount = {}
+        self.maxRatingsInPortion = {}
+        self.maxRowsInPortion = {}
+        self.rowlists = {}
+        self.rowsets = {}
+        self.my_portions = {}
+        self.workers = []
+        self.rmse = float("nan")
+        self.predAvg = float("nan")
+        self.history = []
+        self.completedPortions = 0
+        self.rSumDiff2 = self.rCnt = self.rSum = 0.0
+        self._lastRmseMsg = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # ---- prepare ---------------------------------------------------------------------------
+    def splitDataForTrain(self):
+        """EmfLord.splitDataForTrain (EmfLord.js:39-43): splitToSets -> getStats -> splitToPortions."""
+        t, o = self.table, self.options
+        if not (t.dataset_type != 0).any():
+            fe.split_sets(t, o["dataSetDistr"], seed=o["seed"] + 1)
+        self.totalUsersCount, self.totalItemsCount = t.users, t.items   # max(id), Q5
+        cu, ci = t.counts_per_user(), t.counts_per_item()
+        self.stats = {
+            "ratingsCntPerUser": cu, "ratingsCntPerItem": ci,
+            "maxRatingsPerUser": int(cu.max()), "maxRatingsPerItem": int(ci.max()),
+            "trainUsersRatingsCount": int(cu.sum(dtype=np.int64)),
+            "trainItemsRatingsCount": int(ci.sum(dtype=np.int64)),
+            "totalRatingsAvg": t.total_ratings_avg(),
+        }
+        nthr = o["numThreadsForTrain"]["als"]
+        d = o["dataSetDistr"]
+        for step, cnt, rip, pct in (
+                ("byUser", cu, o["ratingsInPortionForAls"]["byUser"], 0),
+                ("byItem", ci, o["ratingsInPortionForAls"]["byItem"], 0),
+                ("rmseValidate", cu, o["ratingsInPortionForRmse"], d[1] + 1),
+                ("rmseTest", cu, o["ratingsInPortionForRmse"], d[2] + 1)):
+            pto, mr, mrows = fe.split_to_portions(cnt, rip, nthr, pct)
+            self.portionsRowIdTo[step] = pto
+            self.portionsCount[step] = len(pto)
+            self.maxRatingsInPortion[step] = mr
+            self.maxRowsInPortion[step] = mrows
+
+    def _csr(self, step):
+        if step == "byItem":
+            return self.table.csr_by_item(STEP_MASK[step])
+        return self.table.csr_by_user(STEP_MASK[step])
+
+    def _slice_portions(self, step):
+        """Contiguous, nnz-balanced slice of the portion list for this rank."""
+        pto = self.portionsRowIdTo[step]
+        n = len(pto)
+        if self.world == 1 or n == 0:
+            return 0, n
+        ptr = self._csr(step).ptr
+        ends = ptr[np.asarray(pto, np.int64)]            # cumulative ratings at each portion end
+        cuts = ydist.balanced_cuts(ends, self.world)
+        return int(cuts[self.rank]), int(cuts[self.rank + 1])
+
+    def prepareToTrain(self, userFactors=None, itemFactors=None):
+        o = self.options
+        self.splitDataForTrain()
+        if userFactors is not None:
+            self.openSharedFactors(userFactors, itemFactors)      # warm start (EmfManager.js:405-457)
+        else:
+            self.createSharedFactors()
+            self.initSharedFactorsRandom()
+        for step in ("byUser", "byItem", "rmseValidate", "rmseTest"):
+            self.my_portions[step] = self._slice_portions(step)
+        # worker + portion buffers (EmfMaster.js:156-234: Int32[2*maxRows+1], Int32/Float32[maxRatings])
+        mra = max(self.maxRatingsInPortion["byUser"], self.maxRatingsInPortion["byItem"])
+        mrow = max(self.maxRowsInPortion["byUser"], self.maxRowsInPortion["byItem"])
+        mrr = max(self.maxRatingsInPortion["rmseValidate"], self.maxRatingsInPortion["rmseTest"])
+        mrowr = max(self.maxRowsInPortion["rmseValidate"], self.maxRowsInPortion["rmseTest"])
+        pb = {
+            "alsRows": np.zeros(2 * mrow + 1, np.int32), "alsIndx": np.zeros(mra, np.int32),
+            "alsVals": np.zeros(mra, np.float32),
+            "rmseRows": np.zeros(2 * mrowr + 1, np.int32), "rmseIndx": np.zeros(mrr, np.int32),
+            "rmseVals": np.zeros(mrr, np.float32),
+        }
+        wp, mp = EmfProcess(), EmfProcess()
+        wp.peer, mp.peer = mp, wp
+        mp.on("completedPortion", self.wm_completedPortion)
+        mp.on("preparedToTrain", lambda d: None)
+        mp.on("endedTrainStep", lambda d: None)
+        w = EmfWorker(0, wp, o)
+        w.master_side = mp
+        self.workers = [w]
+        mp.emit("prepareToTrain", {
+            "stats": {"totalRatingsAvg": self.stats["totalRatingsAvg"]},
+            "options": o, "totalUsersCount": self.totalUsersCount, "totalItemsCount": self.totalItemsCount,
+            "shared": {"userFactors": self.userFactors, "itemFactors": self.itemFactors, "portionBuffer": pb},
+        })
+        self.ctx = w.ctx
+        mp.emit("startTrain")
+        if o["gpu"]["bulk"]:
+            self.prepareBulk()
+        return self
+
+    def prepareBulk(self):
+        """Upload every step's portions once as a device-resident row set."""
+        for step in ("byUser", "byItem", "rmseValidate", "rmseTest"):
+            csr = self._csr(step)
+            lo, hi = self.my_portions[step]
+            pto = np.asarray(self.portionsRowIdTo[step], np.int32)
+            rl = fe.build_rowlist(csr, pto)
+            r0, r1 = int(rl.portion_first[lo]), int(rl.portion_first[hi])
+            ids, start, ln = rl.row_ids[r0:r1], rl.row_start[r0:r1], rl.row_len[r0:r1]
+            # upload only this rank's span of the ratings arrays
+            if len(ids):
+                s0 = int(start[0])
+                s1 = int((start + ln).max())
+            else:
+                s0 = s1 = 0
+            pf = (rl.portion_first[lo:hi + 1] - r0).astype(np.int32)
+            rid = self.ctx.rowset_create(native.STEP_TYPES[step], np.ascontiguousarray(ids),
+                                         np.ascontiguousarray(start - s0), np.ascontiguousarray(ln),
+                                         csr.idx[s0:s1], csr.vals[s0:s1], pf if len(pf) > 1 else None)
+            self.rowlists[step] = (ids, ln, pf)
+            self.rowsets[step] = rid
+
+    def endTrain(self):
+        for w in self.workers:
+            w.master_side.emit("endTrain")
+        self.workers = []
+        self.ctx = None
+
+    # ---- ALS half-step ------------------------------------------------------------------------
+    def _solved_range(self, step):
+        """Row-id range [lo, hi) this rank solves in `step` (contiguous by construction)."""
+        lo, hi = self.my_portions[step]
+        pto = self.portionsRowIdTo[step]
+        a = 0 if lo == 0 else int(pto[lo - 1])
+        b = a if hi == lo else int(pto[hi - 1])
+        return a, b
+
+    def alsTrainStep(self, stepType):
+        """EmfLord.alsTrainStep (EmfLord.js:963-984)."""
+        mp = self.workers[0].master_side
+        if self.options["gpu"]["bulk"]:
+            self.ctx.als_rowset(self.rowsets[stepType])
+        else:
+            csr = self._csr(stepType)
+            pto = self.portionsRowIdTo[stepType]
+            lo, hi = self.my_portions[stepType]
+            pb = self.workers[0].portionBuffer
+            self.completedPortions = 0
+            mp.emit("startTrainStep", {"stepType": stepType})
+            for p in range(lo, hi):
+                row_from = 0 if p == 0 else int(pto[p - 1])
+                # fill the worker's buffer (EmfMaster.js:571-614, 656-658)
+                fetched = fe.build_portion_into(csr, row_from, int(pto[p]), pb["alsRows"], pb["alsIndx"], pb["alsVals"])
+                self.h2d_bytes += 8 * fetched + 4 * (2 * int(pb["alsRows"][0]) + 1)
+                mp.emit("calcTrainAlsPortion", {"portionNo": p})
+            mp.emit("endTrainStep")
+            a, b = self._solved_range(stepType)
+            self.d2h_bytes += (b - a) * self.factorsCount * 4
+        if self.world > 1:
+            self._refresh_replicas(stepType)
+
+    def _refresh_replicas(self, stepType):
+        which = native.USER_FACTORS if stepType == "byUser" else native.ITEM_FACTORS
+        ranges = ydist.all_ranges(self._solved_range(stepType), self.world, self.group)
+        ydist.refresh_replicas(self.ctx, which, self.factorsCount, ranges, self.rank, self.group,
+                               host=None if self.options["gpu"]["bulk"] else
+                               (self.userFactors if which == 0 else self.itemFactors))
+
+    def alsTrainIter(self):
+        """EmfLord.alsTrainIter (EmfLord.js:954-958)."""
+        self.alsTrainStep("byUser")
+        self.alsTrainStep("byItem")
+
+    # ---- RMSE --------------------------------------------------------------------------------
+    def wm_completedPortion(self, msg):
+        """EmfMaster.m_completedPortion (EmfMaster.js:757-786), accumulation part."""
+        self.completedPortions += 1
+        if "rSumDiff2" in msg:
+            self.rSumDiff2 += msg["rSumDiff2"]
+            self.rCnt += msg["rCnt"]
+            self.rSum += msg["rSum"]
+            self._lastRmseMsg = msg
+
+    def calcRmse(self, stepType, useGlobalAvgShift):
+        """EmfLord.calcRmse (EmfLord.js:1043-1081) + EmfMaster._startCalcRmse (389-412)."""
+        d = self.options["dataSetDistr"]
+        if (d[1] == 0 and stepType == "rmseValidate") or (d[2] == 0 and stepType == "rmseTest"):
+            return None
+        calcGlobalAvgShift = not useGlobalAvgShift
+        if calcGlobalAvgShift:
+            self.globalAvgShift = 0.0
+        self.rSum = self.rSumDiff2 = self.rCnt = 0.0
+        self._lastRmseMsg = None
+        lo, hi = self.my_portions[stepType]
+        if self.options["gpu"]["bulk"]:
+            if hi > lo:
+                tot, ps = self.ctx.rmse_rowset(self.rowsets[stepType], self.globalAvgShift, hi - lo)
+                self.rSumDiff2, self.rCnt, self.rSum = tot
+                self._lastRmseMsg = {"rSum": ps[-1, 2], "rCnt": ps[-1, 1]}
+        else:
+            mp = self.workers[0].master_side
+            csr = self._csr(stepType)
+            pto = self.portionsRowIdTo[stepType]
+            pb = self.workers[0].portionBuffer
+            mp.emit("startCalcRmse", {"stepType": stepType, "globalAvgShift": self.globalAvgShift})
+            for p in range(lo, hi):
+                row_from = 0 if p == 0 else int(pto[p - 1])
+                fetched = fe.build_portion_into(csr, row_from, int(pto[p]), pb["rmseRows"], pb["rmseIndx"], pb["rmseVals"])
+                self.h2d_bytes += 8 * fetched + 4 * (2 * int(pb["rmseRows"][0]) + 1)
+                mp.emit("calcRmsePortion", {"portionNo": p})
+                self.d2h_bytes += 24
+        last = self._lastRmseMsg
+        if self.world > 1:   # 'rmseSaveCalcs' reduce-to-root + the last portion's partials (Q7)
+            (self.rSumDiff2, self.rCnt, self.rSum), last = ydist.reduce_rmse(
+                (self.rSumDiff2, self.rCnt, self.rSum), last, self.group)
+        self.rmse = math.sqrt(1.0 * self.rSumDiff2 / self.rCnt) if self.rCnt else float("nan")
+        # Q7: predAvg from the LAST completed portion's message (EmfMaster.js:779)
+        self.predAvg = last["rSum"] / last["rCnt"] if last and last["rCnt"] else float("nan")
+        if calcGlobalAvgShift:
+            self.globalAvgShift = self.stats["totalRatingsAvg"] - self.predAvg
+        return self.rmse
+
+    # ---- train loop ------------------------------------------------------------------------------
+    def trainIter(self):
+        """One pass of the loop body of EmfLord.train (EmfLord.js:892-902)."""
+        self.alsTrainIter()
+        out = {
+            "rmseValidate": self.calcRmse("rmseValidate", False),
+            "rmseTest": self.calcRmse("rmseTest", False),
+            "rmseTestShift": self.calcRmse("rmseTest", True),
+            "globalAvgShift": self.globalAvgShift,
+        }
+        self.history.append(out)
+        return out
+
+    def train(self, iters=None):
+        for _ in range(self.options["trainIters"] if iters is None else iters):
+            self.trainIter()
+        if self.options["gpu"]["bulk"]:
+            self.syncFactorsToHost()
+        return self.history
+
+    def syncFactorsToHost(self):
+        """Bulk mode keeps the factors on the device; copy both matrices into the host segments."""
+        self.ctx.download_factors(native.USER_FACTORS)
+        self.ctx.download_factors(native.ITEM_FACTORS)
+        self.d2h_bytes += (self.totalUsersCount + self.totalItemsCount) * self.factorsCount * 4

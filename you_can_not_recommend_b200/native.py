@@ -1,0 +1,220 @@
+"""ctypes binding of libycnr_als.so (include/ycnr_als.h) — the same C ABI the N-API shim binds.
+
+Loading the library never touches the GPU; every compute call fails loudly (RuntimeError
+carrying ycnr_last_error()) when no B200 is usable.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import build
+
+BY_USER, BY_ITEM, RMSE_VALIDATE, RMSE_TEST = 0, 1, 2, 3
+USER_FACTORS, ITEM_FACTORS = 0, 1
+GRAM_AUTO, GRAM_FFMA, GRAM_TC3XTF32 = 0, 1, 2
+STEP_TYPES = {"byUser": BY_USER, "byItem": BY_ITEM, "rmseValidate": RMSE_VALIDATE, "rmseTest": RMSE_TEST}
+
+KERNEL_CLASSES = ["primal_fused", "dual_fused", "gram_partial", "reduce_solve", "rmse_rows", "rmse_reduce",
+                  "gather", "gram_tc"]
+
+# every symbol include/ycnr_als.h declares (tests/test_abi.py checks the export table)
+EXPORTS = [
+    "ycnr_last_error", "ycnr_device_count", "ycnr_create", "ycnr_destroy", "ycnr_attach_factors",
+    "ycnr_upload_factors", "ycnr_download_factors", "ycnr_invalidate_device", "ycnr_device_factors",
+    "ycnr_stream", "ycnr_synchronize", "ycnr_start_train_step", "ycnr_als_portion", "ycnr_end_train_step",
+    "ycnr_start_calc_rmse", "ycnr_rmse_portion", "ycnr_s_als_build_sub_fixed_facts", "ycnr_rowset_create",
+    "ycnr_rowset_destroy", "ycnr_als_rowset", "ycnr_rmse_rowset", "ycnr_ipc_export", "ycnr_ipc_import",
+    "ycnr_ipc_close", "ycnr_set_peers", "ycnr_profile_reset", "ycnr_profile_read",
+]
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("factors_count", C.c_int32), ("total_users", C.c_int32), ("total_items", C.c_int32),
+        ("user_fact_reg", C.c_double), ("item_fact_reg", C.c_double),
+        ("use_double_precision", C.c_int32), ("lowmem", C.c_int32), ("device", C.c_int32),
+        ("gram_path", C.c_int32), ("dual_max_cols", C.c_int32), ("split_cols", C.c_int32),
+        ("profile", C.c_int32), ("reserved", C.c_int32 * 4),
+    ]
+
+
+class PortionInfo(C.Structure):
+    _fields_ = [
+        ("rows_from", C.c_int32), ("rows_cnt", C.c_int32), ("ratings_in_portion", C.c_int64),
+        ("time_ms", C.c_double), ("r_sum_diff2", C.c_double), ("r_cnt", C.c_double), ("r_sum", C.c_double),
+    ]
+
+
+class Profile(C.Structure):
+    _fields_ = [
+        ("ms", C.c_double * 8), ("launches", C.c_int64 * 8), ("rows", C.c_int64 * 8),
+        ("ratings", C.c_int64 * 8), ("total_launches", C.c_int64),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Build (if stale) and load libycnr_als.so."""
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build.build_cuda())
+        L.ycnr_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("ycnr_als: " + lib().ycnr_last_error().decode())
+
+
+def _i32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _i64(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def _f32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def device_count():
+    n = C.c_int32(0)
+    rc = lib().ycnr_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+class Context:
+    """Owns one ycnr_ctx (one GPU). Thin: argument marshalling only."""
+
+    def __init__(self, factors_count, total_users, total_items, user_fact_reg=0.05, item_fact_reg=0.05,
+                 use_double_precision=False, lowmem=False, device=0, gram_path=GRAM_AUTO, dual_max_cols=-1,
+                 split_cols=0, profile=False):
+        o = Options()
+        o.factors_count, o.total_users, o.total_items = factors_count, total_users, total_items
+        o.user_fact_reg, o.item_fact_reg = user_fact_reg, item_fact_reg
+        o.use_double_precision, o.lowmem, o.device = int(use_double_precision), int(lowmem), device
+        o.gram_path, o.dual_max_cols, o.split_cols, o.profile = gram_path, dual_max_cols, split_cols, int(profile)
+        self._h = C.c_void_p()
+        self.k, self.total_users, self.total_items = factors_count, total_users, total_items
+        self._keep = []
+        _check(lib().ycnr_create(C.byref(o), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().ycnr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # -- factor store
+    def attach_factors(self, user_factors, item_factors):
+        for a, rows in ((user_factors, self.total_users), (item_factors, self.total_items)):
+            assert a.dtype == np.float32 and a.flags.c_contiguous and a.shape == (rows, self.k)
+        self._keep = [user_factors, item_factors]
+        _check(lib().ycnr_attach_factors(self._h, _f32(user_factors), _f32(item_factors)))
+
+    def upload_factors(self, which):
+        _check(lib().ycnr_upload_factors(self._h, C.c_int32(which)))
+
+    def download_factors(self, which, row_from=0, row_cnt=-1):
+        _check(lib().ycnr_download_factors(self._h, C.c_int32(which), C.c_int32(row_from), C.c_int32(row_cnt)))
+
+    def invalidate_device(self, which):
+        _check(lib().ycnr_invalidate_device(self._h, C.c_int32(which)))
+
+    def device_factors_ptr(self, which):
+        p = C.c_void_p()
+        _check(lib().ycnr_device_factors(self._h, C.c_int32(which), C.byref(p)))
+        return p.value
+
+    def stream_ptr(self):
+        p = C.c_void_p()
+        _check(lib().ycnr_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def synchronize(self):
+        _check(lib().ycnr_synchronize(self._h))
+
+    # -- per-portion path
+    def start_train_step(self, step_type):
+        _check(lib().ycnr_start_train_step(self._h, C.c_int32(step_type)))
+
+    def als_portion(self, rows, indx, vals):
+        info = PortionInfo()
+        _check(lib().ycnr_als_portion(self._h, _i32(rows), _i32(indx), _f32(vals), C.byref(info)))
+        return info
+
+    def end_train_step(self):
+        _check(lib().ycnr_end_train_step(self._h))
+
+    def start_calc_rmse(self, step_type, global_avg_shift):
+        _check(lib().ycnr_start_calc_rmse(self._h, C.c_int32(step_type), C.c_double(global_avg_shift)))
+
+    def rmse_portion(self, rows, indx, vals):
+        info = PortionInfo()
+        _check(lib().ycnr_rmse_portion(self._h, _i32(rows), _i32(indx), _f32(vals), C.byref(info)))
+        return info
+
+    def build_sub_fixed_facts(self, sub, fixed, indx):
+        k = fixed.shape[1]
+        _check(lib().ycnr_s_als_build_sub_fixed_facts(self._h, _f32(sub), _f32(fixed), C.c_int64(fixed.shape[0]),
+                                                      _i32(indx), C.c_int32(len(indx)), C.c_int32(k)))
+
+    # -- bulk path
+    def rowset_create(self, step_type, row_ids, row_start, row_len, indx, vals, portion_first=None):
+        rid = C.c_int32(-1)
+        npor = 0 if portion_first is None else len(portion_first) - 1
+        _check(lib().ycnr_rowset_create(
+            self._h, C.c_int32(step_type), C.c_int32(len(row_ids)), _i32(row_ids), _i64(row_start), _i32(row_len),
+            _i32(indx), _f32(vals), C.c_int64(len(indx)),
+            None if portion_first is None else _i32(portion_first), C.c_int32(npor), C.byref(rid)))
+        return rid.value
+
+    def rowset_destroy(self, rowset):
+        _check(lib().ycnr_rowset_destroy(self._h, C.c_int32(rowset)))
+
+    def als_rowset(self, rowset):
+        _check(lib().ycnr_als_rowset(self._h, C.c_int32(rowset)))
+
+    def rmse_rowset(self, rowset, shift, n_portions=0):
+        totals = (C.c_double * 3)()
+        psums = np.zeros((max(n_portions, 1), 3), np.float64)
+        _check(lib().ycnr_rmse_rowset(self._h, C.c_int32(rowset), C.c_double(shift), totals,
+                                      psums.ctypes.data_as(C.POINTER(C.c_double)) if n_portions else None))
+        return (totals[0], totals[1], totals[2]), psums
+
+    # -- multi-GPU
+    def ipc_export(self, which):
+        buf = (C.c_uint8 * 64)()
+        _check(lib().ycnr_ipc_export(self._h, C.c_int32(which), buf))
+        return bytes(buf)
+
+    def ipc_import(self, handle):
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        _check(lib().ycnr_ipc_import(self._h, buf, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        _check(lib().ycnr_ipc_close(self._h, C.c_void_p(ptr)))
+
+    def set_peers(self, which, ptrs):
+        arr = (C.c_void_p * max(1, len(ptrs)))(*ptrs)
+        _check(lib().ycnr_set_peers(self._h, C.c_int32(which), C.c_int32(len(ptrs)), arr))
+
+    # -- measurement
+    def profile_reset(self):
+        _check(lib().ycnr_profile_reset(self._h))
+
+    def profile_read(self):
+        p = Profile()
+        _check(lib().ycnr_profile_read(self._h, C.byref(p)))
+        out = {name: dict(ms=p.ms[i], launches=p.launches[i], rows=p.rows[i], ratings=p.ratings[i])
+               for i, name in enumerate(KERNEL_CLASSES)}
+        out["total_launches"] = p.total_launches
+        return out
