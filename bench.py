@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — ALS ratings/sec per iteration (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mal|netflix|ml-1m|ml-100k]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      # the reference's CPU path (multi-threaded BLAS port)
+
+A step is one full ALS iteration of the reference train loop (EmfLord.js:892-902): byUser
+half-step, byItem half-step, RMSE(validate), RMSE(test), RMSE(test, shift applied), over
+synthetic ratings of the named shape.  `value` = dataset ratings / seconds per iteration with
+every input resident in HBM (bulk row sets); `e2e` = the same iteration driven through the
+worker's per-portion messages with HOST portion buffers and the solved factor rows read back
+into the host factor segments every half-step.  Rank 0 prints one JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "als_ratings_per_sec_per_iteration"
+UNIT = "ratings/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mal", choices=["mal", "netflix", "ml-1m", "ml-100k"])
+    ap.add_argument("--factors", type=int, default=0)
+    ap.add_argument("--e2e-portion", type=int, default=2_000_000, help="ratingsInPortionForAls of the e2e leg")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fused-peers", action="store_true", help="solve kernels store rows into peer replicas")
+    ap.add_argument("--gram", default="auto", choices=["auto", "ffma", "tc"])
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def build_table(args):
+    from you_can_not_recommend_b200 import front_end as fe
+    t = fe.synth_table(args.workload)
+    k = args.factors or fe.SHAPES[args.workload]["factors"]
+    return t, k
+
+
+class CpuArm:
+    """The reference's CPU implementation of the path: per-row gather -> sgemm(T,N) -> +lambda*n*I ->
+    sgemv -> sgesv through multi-threaded OpenBLAS (oracle O32), timed on an evenly
+    spread sample of 10k-rating portions of both half-steps and extrapolated linearly to the dataset."""
+
+    def __init__(self, table, k):
+        from oracle import oracle
+        from you_can_not_recommend_b200 import front_end as fe
+        from you_can_not_recommend_b200.emf_master import EmfMaster
+        self.oracle, self.fe, self.table, self.k = oracle, fe, table, k
+        self.cores = os.cpu_count() or 1
+        self.have_blas = oracle.set_blas(threads=self.cores)
+        self.m = EmfMaster(table, {"factorsCount": k})
+        self.m.splitDataForTrain()
+        self.U = fe.init_factors(table.users, k, 0)
+        self.V = fe.init_factors(table.items, k, 1)
+        self.nnz12 = self.m._csr("byUser").nnz
+        self.m._csr("byItem")
+
+    def sample(self, seconds, offset=0):
+        m, fe, oracle = self.m, self.fe, self.oracle
+        per_rating, desc = {}, []
+        for step in ("byUser", "byItem"):
+            csr = m._csr(step)
+            pto = m.portionsRowIdTo[step]
+            fixed, solved = (self.V, self.U) if step == "byUser" else (self.U, self.V)
+            n_por = len(pto)
+            stride = max(1, n_por // 64)                      # evenly spread over the id range
+            mr, mrow = m.maxRatingsInPortion[step], m.maxRowsInPortion[step] + 1
+            done_r, t_used, used = 0, 0.0, 0
+            p = offset % stride
+            while p < n_por and t_used < seconds / 2:
+                rows, indx, vals, _ = fe.build_portion(csr, 0 if p == 0 else int(pto[p - 1]), int(pto[p]), mrow, mr)
+                t0 = time.perf_counter()
+                done_r += oracle.als_portion(rows, indx, vals, fixed, solved, 0.05, use_blas=self.have_blas)
+                t_used += time.perf_counter() - t0
+                used += 1
+                p += stride
+            per_rating[step] = t_used / max(done_r, 1)
+            desc.append("%s: %d of %d portions (%d ratings, %.1f s)" % (step, used, n_por, done_r, t_used))
+        iter_s = self.nnz12 * (per_rating["byUser"] + per_rating["byItem"])
+        return {
+            "value": self.table.nnz / iter_s, "unit": UNIT, "cores": self.cores, "kind": "port",
+            "sample": "; ".join(desc) + "; extrapolated linearly to %d train+validate ratings; RMSE passes excluded" % self.nnz12,
+            "blas": "openblas(scipy), %d threads" % self.cores if self.have_blas else "portable C loops",
+            "iter_seconds_extrapolated": iter_s,
+        }
+
+
+def run_reference(args):
+    """--impl reference: rank 0 times the CPU port; a step is one bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    table, k = build_table(args)
+    arm = CpuArm(table, k)
+    vals, cb = [], None
+    per_step = max(1.0, args.cpu_seconds / max(1, args.steps))
+    for i in range(args.warmup + args.steps):
+        cb = arm.sample(per_step if i >= args.warmup else min(per_step, 2.0), offset=i)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = statistics.mean(vals) if vals else cb["value"]
+    cb = dict(cb, value=v)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * table.nnz / v, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "users": table.users, "items": table.items, "ratings": table.nnz,
+                   "factors": k, "note": "CPU port of the reference path (oracle O32 over OpenBLAS), sample extrapolated"},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from you_can_not_recommend_b200 import dist as ydist
+    from you_can_not_recommend_b200 import native
+    from you_can_not_recommend_b200.emf_master import EmfMaster
+
+    rank, local, world = ydist.init_from_env("nccl")
+    if world != args.gpus:
+        if rank == 0 and world == 1 and args.gpus > 1:
+            sys.stderr.write("bench.py: --gpus %d needs torchrun with %d ranks\n" % (args.gpus, args.gpus))
+            sys.exit(2)
+    if native.device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device — the ALS hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    table, k = build_table(args)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---------------- device-resident iterations (value) ----------------
+    opts = {"factorsCount": k, "gpu": {"bulk": True, "profile": True, "device": local, "gramPath": args.gram}}
+    m = EmfMaster(table, opts, rank=rank, world=world)
+    m.prepareToTrain()
+    if world > 1 and args.fused_peers:
+        for which in (native.USER_FACTORS, native.ITEM_FACTORS):
+            ydist.connect_peers(m.ctx, which, rank, world)
+    stream = torch.cuda.ExternalStream(m.ctx.stream_ptr(), device=torch.device("cuda", local))
+    for _ in range(args.warmup):
+        m.trainIter()
+    m.ctx.synchronize()
+    torch.cuda.synchronize()
+    barrier()
+    m.ctx.profile_reset()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    hist = []
+    for _ in range(args.steps):
+        hist.append(m.trainIter())
+    e1.record(stream)
+    m.ctx.synchronize()
+    torch.cuda.synchronize()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = m.ctx.profile_read()
+    ms = max(dev_ms, 0.0)
+    if world > 1:
+        tmax = torch.tensor([ms, wall_ms], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms, wall_ms = float(tmax[0]), float(tmax[1])
+        launches = torch.tensor([prof["total_launches"]], device="cuda", dtype=torch.int64)
+        dist.all_reduce(launches)
+        total_launches = int(launches[0])
+    else:
+        total_launches = int(prof["total_launches"])
+    ms_per_step = ms / args.steps
+    value = table.nnz / (ms_per_step / 1e3)
+    nnz_by = {s: int(m.rowlists[s][1].sum(dtype=np.int64)) for s in ("byUser", "byItem")}
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peak, peak_src = measured_peaks()
+    gram_classes = ["primal_fused", "dual_fused", "gram_partial", "gram_tc"]
+    dom = max(native.KERNEL_CLASSES, key=lambda c: prof[c]["ms"])
+    roof = None
+    if prof[dom]["launches"] > 0 and prof[dom]["ms"] > 0:
+        per_launch_ms = prof[dom]["ms"] / prof[dom]["launches"]
+        ratings_per_launch = prof[dom]["ratings"] / prof[dom]["launches"]
+        alg_bytes = ratings_per_launch * k * 4                  # B_gather = nnz * k * 4
+        alg_flops = ratings_per_launch * k * k                  # F_gram = nnz * k^2 (symmetric-aware)
+        achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                "launch_ms": per_launch_ms, "launches_timed": prof[dom]["launches"],
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "gram_tflops": alg_flops / (per_launch_ms * 1e-3) / 1e12,
+                "share_of_step": prof[dom]["ms"] / ms if ms > 0 else None}
+    kernels = {c: {"ms_per_step": prof[c]["ms"] / args.steps, "launches_per_step": prof[c]["launches"] / args.steps,
+                   "rows_per_step": prof[c]["rows"] / args.steps, "ratings_per_step": prof[c]["ratings"] / args.steps}
+               for c in native.KERNEL_CLASSES if prof[c]["launches"]}
+    last = hist[-1] if hist else {}
+    m.endTrain()
+    del m
+
+    # ---------------- e2e: worker messages with host portion buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        opts2 = {"factorsCount": k,
+                 "ratingsInPortionForAls": {"byUser": args.e2e_portion, "byItem": args.e2e_portion},
+                 "ratingsInPortionForRmse": args.e2e_portion,
+                 "gpu": {"bulk": False, "profile": False, "device": local, "gramPath": args.gram}}
+        m2 = EmfMaster(table, opts2, rank=rank, world=world)
+        m2.prepareToTrain()
+        for _ in range(max(1, min(args.warmup, 2))):
+            m2.trainIter()
+        m2.ctx.synchronize()
+        torch.cuda.synchronize()
+        barrier()
+        m2.h2d_bytes = m2.d2h_bytes = 0
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            m2.trainIter()
+        m2.ctx.synchronize()
+        torch.cuda.synchronize()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        h2d, d2h = m2.h2d_bytes / n_e2e, m2.d2h_bytes / n_e2e
+        if world > 1:
+            tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt[0])
+            bb = torch.tensor([h2d, d2h], device="cuda", dtype=torch.float64)
+            dist.all_reduce(bb)
+            h2d, d2h = float(bb[0]), float(bb[1])
+        e2e = {"value": table.nnz / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "ratings_in_portion": args.e2e_portion,
+               "api": "EmfWorker calcTrainAlsPortion/calcRmsePortion messages -> ycnr_als_portion/ycnr_rmse_portion"}
+        m2.endTrain()
+        del m2
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = CpuArm(table, k).sample(args.cpu_seconds)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "users": table.users, "items": table.items, "ratings": table.nnz,
+                       "factors": k, "train_ratings_per_half_step": nnz_by, "split": [85, 10, 5],
+                       "ratings_in_portion": 10000, "parallelism": "rows nnz-balanced over %d GPU(s)" % world,
+                       "replica_refresh": ("peer stores from the solve kernels" if args.fused_peers else "NCCL broadcast per rank slice") if world > 1 else "none",
+                       "l2": "inputs_exceed_l2 (CSR + factors >> 126 MB)", "gram_path": args.gram,
+                       "step": "byUser + byItem + 3 RMSE passes"},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches,
+            "clocks": clocks, "rmse": last,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

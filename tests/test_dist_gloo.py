@@ -1,0 +1,76 @@
+"""Host-side multi-rank logic on CPU: world_size 2 over gloo (rendezvous on 127.0.0.1)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from you_can_not_recommend_b200 import dist as ydist
+
+
+def test_balanced_cuts_properties():
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 4, 8):
+        sizes = rng.integers(1, 1000, 97)
+        ends = np.cumsum(sizes)
+        cuts = ydist.balanced_cuts(ends, world)
+        assert cuts[0] == 0 and cuts[-1] == len(ends) and (np.diff(cuts) >= 0).all()
+        per = [int(sizes[cuts[r]:cuts[r + 1]].sum()) for r in range(world)]
+        assert sum(per) == int(ends[-1])
+        assert max(per) - min(per) <= 2 * sizes.max()
+    assert list(ydist.balanced_cuts(np.asarray([5]), 4)) in ([0, 0, 0, 1, 1], [0, 1, 1, 1, 1], [0, 0, 1, 1, 1])
+    assert list(ydist.balanced_cuts(np.zeros(0, np.int64), 2)) == [0, 0, 0]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, _, w = ydist.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    rows, k = 10, 4
+    # every rank starts from the same replica and "solves" its own contiguous row range
+    mat = torch.arange(rows * k, dtype=torch.float32).reshape(rows, k).clone()
+    cuts = ydist.balanced_cuts(np.asarray([3, 4, 8, 10]), world)       # 4 portions -> row ends 3,4,8,10
+    pto = [3, 4, 8, 10]
+    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+    a = 0 if lo == 0 else pto[lo - 1]
+    b = a if hi == lo else pto[hi - 1]
+    mat[a:b] = -(rank + 1)
+    ranges = ydist.all_ranges((a, b), world)
+    ydist.broadcast_ranges(mat, ranges)
+    sums, last = ydist.reduce_rmse((1.0 + rank, 10.0 * (rank + 1), 0.5), {"rSum": float(rank), "rCnt": 2.0} if rank == 0 or hi > lo else None)
+    q.put((rank, ranges, mat.numpy().copy(), sums, last))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_exchange_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ranges = res[0][1]
+    assert ranges == res[1][1] and ranges[0][0] == 0 and ranges[0][1] == ranges[1][0] and ranges[1][1] == 10
+    assert (res[0][2] == res[1][2]).all()                       # replicas identical after the exchange
+    for r, (a, b) in enumerate(ranges):
+        assert (res[0][2][a:b] == -(r + 1)).all()
+    assert res[0][3] == res[1][3] == (3.0, 30.0, 1.0)
+    assert res[0][4] == res[1][4] == {"rSum": 1.0, "rCnt": 2.0}   # last portion lives on the highest rank
