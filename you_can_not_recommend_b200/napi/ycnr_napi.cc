@@ -1,0 +1,239 @@
+// ycnr_napi.cc — thin N-API shim over the C ABI of libycnr_als.so (include/ycnr_als.h).
+//
+// Takes the slot of the reference's raw-V8 addon (cpp_utils/cpp_utils.cc:3-8, built by
+// binding.gyp:4-9 as build/Release/cpp_utils): the module keeps the two upstream exports
+//   sAlsBuildSubFixedFacts(sub, fixed, indx, cols, k)   (cpp_utils/als_utils.cc:22-38)
+//   dAlsBuildSubFixedFacts(...)                         (float64: rejected, GPU path is float32)
+// and adds the calls EmfWorker's portion handlers make instead of their BLAS/LAPACK loops
+// (lib/emf/EmfWorker.js:169-261, 266-315).  No arithmetic here: argument marshalling and
+// status -> thrown Error only, so the worker's uncaughtException path fires on failure
+// (lib/emf/EmfWorkerProcess.js:30-45).  Cannot be executed in this image (no node); it is
+// syntax-checked against node_api_min.h by tests/test_napi_syntax.py.
+#ifdef YCNR_NAPI_MIN
+#include "node_api_min.h"
+#else
+#include <node_api.h>
+#endif
+#include <stdint.h>
+#include <string.h>
+
+#include "ycnr_als.h"
+
+namespace {
+
+bool fail(napi_env env, const char* what) {
+  napi_throw_error(env, "YCNR", what);
+  return false;
+}
+bool check(napi_env env, int rc) { return rc == 0 ? true : fail(env, ycnr_last_error()); }
+
+bool args(napi_env env, napi_callback_info info, size_t want, napi_value* argv) {
+  size_t argc = want;
+  if (napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr) != napi_ok || argc < want)
+    return fail(env, "wrong number of arguments");
+  return true;
+}
+
+template <class T>
+bool typed(napi_env env, napi_value v, napi_typedarray_type want, T** data, size_t* len) {
+  napi_typedarray_type t;
+  void* p = nullptr;
+  if (napi_get_typedarray_info(env, v, &t, len, &p, nullptr, nullptr) != napi_ok || t != want)
+    return fail(env, "invalid type!");  // message of cpp_utils.js:13
+  *data = static_cast<T*>(p);
+  return true;
+}
+
+bool handle(napi_env env, napi_value v, ycnr_ctx** out) {
+  void* p = nullptr;
+  if (napi_get_value_external(env, v, &p) != napi_ok || !p) return fail(env, "invalid context handle");
+  *out = static_cast<ycnr_ctx*>(p);
+  return true;
+}
+
+napi_value undefined(napi_env env) {
+  napi_value u;
+  napi_get_undefined(env, &u);
+  return u;
+}
+
+double get_num(napi_env env, napi_value obj, const char* name, double dflt) {
+  bool has = false;
+  napi_value v;
+  double d = dflt;
+  if (napi_has_named_property(env, obj, name, &has) == napi_ok && has &&
+      napi_get_named_property(env, obj, name, &v) == napi_ok)
+    napi_get_value_double(env, v, &d);
+  return d;
+}
+bool get_flag(napi_env env, napi_value obj, const char* name) {
+  bool has = false, b = false;
+  napi_value v;
+  if (napi_has_named_property(env, obj, name, &has) == napi_ok && has &&
+      napi_get_named_property(env, obj, name, &v) == napi_ok)
+    napi_get_value_bool(env, v, &b);
+  return b;
+}
+
+void finalize_ctx(napi_env, void* data, void*) { ycnr_destroy(static_cast<ycnr_ctx*>(data)); }
+
+// create({factorsCount, totalUsersCount, totalItemsCount, userFactReg, itemFactReg,
+//         useDoublePrecision, lowmem, device}) -> handle
+napi_value Create(napi_env env, napi_callback_info info) {
+  napi_value a[1];
+  if (!args(env, info, 1, a)) return nullptr;
+  ycnr_options o;
+  memset(&o, 0, sizeof(o));
+  o.factors_count = (int32_t)get_num(env, a[0], "factorsCount", 100);
+  o.total_users = (int32_t)get_num(env, a[0], "totalUsersCount", 0);
+  o.total_items = (int32_t)get_num(env, a[0], "totalItemsCount", 0);
+  o.user_fact_reg = get_num(env, a[0], "userFactReg", 0.05);
+  o.item_fact_reg = get_num(env, a[0], "itemFactReg", 0.05);
+  o.use_double_precision = get_flag(env, a[0], "useDoublePrecision");
+  o.lowmem = get_flag(env, a[0], "lowmem");
+  o.device = (int32_t)get_num(env, a[0], "device", 0);
+  o.dual_max_cols = -1;
+  ycnr_ctx* c = nullptr;
+  if (!check(env, ycnr_create(&o, &c))) return nullptr;
+  napi_value ext;
+  napi_create_external(env, c, finalize_ctx, nullptr, &ext);
+  return ext;
+}
+
+// attachFactors(handle, Float32Array userFactors, Float32Array itemFactors)   (shm-typed-array views)
+napi_value AttachFactors(napi_env env, napi_callback_info info) {
+  napi_value a[3];
+  ycnr_ctx* c;
+  float *u, *v;
+  size_t nu, nv;
+  if (!args(env, info, 3, a) || !handle(env, a[0], &c) || !typed(env, a[1], napi_float32_array, &u, &nu) ||
+      !typed(env, a[2], napi_float32_array, &v, &nv))
+    return nullptr;
+  check(env, ycnr_attach_factors(c, u, v));
+  return undefined(env);
+}
+
+napi_value StartTrainStep(napi_env env, napi_callback_info info) {
+  napi_value a[2];
+  ycnr_ctx* c;
+  int32_t step;
+  if (!args(env, info, 2, a) || !handle(env, a[0], &c) || napi_get_value_int32(env, a[1], &step) != napi_ok) return nullptr;
+  check(env, ycnr_start_train_step(c, step));
+  return undefined(env);
+}
+
+napi_value portion_result(napi_env env, const ycnr_portion_info& pi, bool rmse) {
+  napi_value o, v;
+  napi_create_object(env, &o);
+  napi_create_int32(env, pi.rows_from, &v); napi_set_named_property(env, o, "rowsFrom", v);
+  napi_create_int32(env, pi.rows_cnt, &v); napi_set_named_property(env, o, "rowsCnt", v);
+  napi_create_int64(env, pi.ratings_in_portion, &v); napi_set_named_property(env, o, "ratingsInPortion", v);
+  napi_create_double(env, pi.time_ms, &v); napi_set_named_property(env, o, "time", v);
+  if (rmse) {
+    napi_create_double(env, pi.r_sum_diff2, &v); napi_set_named_property(env, o, "rSumDiff2", v);
+    napi_create_double(env, pi.r_cnt, &v); napi_set_named_property(env, o, "rCnt", v);
+    napi_create_double(env, pi.r_sum, &v); napi_set_named_property(env, o, "rSum", v);
+  }
+  return o;
+}
+
+// alsPortion(handle, Int32Array alsRows, Int32Array alsIndx, Float32Array alsVals) -> completedPortion fields
+napi_value AlsPortion(napi_env env, napi_callback_info info) {
+  napi_value a[4];
+  ycnr_ctx* c;
+  int32_t *rows, *indx;
+  float* vals;
+  size_t n0, n1, n2;
+  if (!args(env, info, 4, a) || !handle(env, a[0], &c) || !typed(env, a[1], napi_int32_array, &rows, &n0) ||
+      !typed(env, a[2], napi_int32_array, &indx, &n1) || !typed(env, a[3], napi_float32_array, &vals, &n2))
+    return nullptr;
+  ycnr_portion_info pi;
+  if (!check(env, ycnr_als_portion(c, rows, indx, vals, &pi))) return nullptr;
+  return portion_result(env, pi, false);
+}
+
+napi_value EndTrainStep(napi_env env, napi_callback_info info) {
+  napi_value a[1];
+  ycnr_ctx* c;
+  if (!args(env, info, 1, a) || !handle(env, a[0], &c)) return nullptr;
+  check(env, ycnr_end_train_step(c));
+  return undefined(env);
+}
+
+napi_value StartCalcRmse(napi_env env, napi_callback_info info) {
+  napi_value a[3];
+  ycnr_ctx* c;
+  int32_t step;
+  double shift;
+  if (!args(env, info, 3, a) || !handle(env, a[0], &c) || napi_get_value_int32(env, a[1], &step) != napi_ok ||
+      napi_get_value_double(env, a[2], &shift) != napi_ok)
+    return nullptr;
+  check(env, ycnr_start_calc_rmse(c, step, shift));
+  return undefined(env);
+}
+
+napi_value RmsePortion(napi_env env, napi_callback_info info) {
+  napi_value a[4];
+  ycnr_ctx* c;
+  int32_t *rows, *indx;
+  float* vals;
+  size_t n0, n1, n2;
+  if (!args(env, info, 4, a) || !handle(env, a[0], &c) || !typed(env, a[1], napi_int32_array, &rows, &n0) ||
+      !typed(env, a[2], napi_int32_array, &indx, &n1) || !typed(env, a[3], napi_float32_array, &vals, &n2))
+    return nullptr;
+  ycnr_portion_info pi;
+  if (!check(env, ycnr_rmse_portion(c, rows, indx, vals, &pi))) return nullptr;
+  return portion_result(env, pi, true);
+}
+
+// sAlsBuildSubFixedFacts(handle, sub, fixed, indx, cols, k) — upstream signature + the context
+napi_value SAlsBuildSubFixedFacts(napi_env env, napi_callback_info info) {
+  napi_value a[6];
+  ycnr_ctx* c;
+  float *sub, *fixed;
+  int32_t* indx;
+  size_t ns, nf, ni;
+  int32_t cols, k;
+  if (!args(env, info, 6, a) || !handle(env, a[0], &c) || !typed(env, a[1], napi_float32_array, &sub, &ns) ||
+      !typed(env, a[2], napi_float32_array, &fixed, &nf) || !typed(env, a[3], napi_int32_array, &indx, &ni) ||
+      napi_get_value_int32(env, a[4], &cols) != napi_ok || napi_get_value_int32(env, a[5], &k) != napi_ok)
+    return nullptr;
+  if (k <= 0 || cols < 0 || (size_t)cols > ni || (size_t)cols * (size_t)k > ns) return fail(env, "buffer too small"), nullptr;
+  check(env, ycnr_s_als_build_sub_fixed_facts(c, sub, fixed, (int64_t)(nf / (size_t)k), indx, cols, k));
+  return undefined(env);
+}
+
+napi_value DAlsBuildSubFixedFacts(napi_env env, napi_callback_info) {
+  fail(env, "useDoublePrecision is not supported by the B200 path (float32 only)");
+  return nullptr;
+}
+
+napi_value Destroy(napi_env env, napi_callback_info info) {
+  // contexts are released by the external's finalizer; explicit destroy only synchronises
+  napi_value a[1];
+  ycnr_ctx* c;
+  if (!args(env, info, 1, a) || !handle(env, a[0], &c)) return nullptr;
+  check(env, ycnr_synchronize(c));
+  return undefined(env);
+}
+
+napi_value Init(napi_env env, napi_value exports) {
+  const napi_property_descriptor props[] = {
+      {"create", nullptr, Create, nullptr, nullptr, nullptr, 0, nullptr},
+      {"attachFactors", nullptr, AttachFactors, nullptr, nullptr, nullptr, 0, nullptr},
+      {"startTrainStep", nullptr, StartTrainStep, nullptr, nullptr, nullptr, 0, nullptr},
+      {"alsPortion", nullptr, AlsPortion, nullptr, nullptr, nullptr, 0, nullptr},
+      {"endTrainStep", nullptr, EndTrainStep, nullptr, nullptr, nullptr, 0, nullptr},
+      {"startCalcRmse", nullptr, StartCalcRmse, nullptr, nullptr, nullptr, 0, nullptr},
+      {"rmsePortion", nullptr, RmsePortion, nullptr, nullptr, nullptr, 0, nullptr},
+      {"sAlsBuildSubFixedFacts", nullptr, SAlsBuildSubFixedFacts, nullptr, nullptr, nullptr, 0, nullptr},
+      {"dAlsBuildSubFixedFacts", nullptr, DAlsBuildSubFixedFacts, nullptr, nullptr, nullptr, 0, nullptr},
+      {"destroy", nullptr, Destroy, nullptr, nullptr, nullptr, 0, nullptr},
+  };
+  napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
+  return exports;
+}
+
+}  // namespace
+
+NAPI_MODULE(cpp_utils, Init)
