@@ -284,7 +284,8 @@ def main():
         opts2 = {"factorsCount": k,
                  "ratingsInPortionForAls": {"byUser": args.e2e_portion, "byItem": args.e2e_portion},
                  "ratingsInPortionForRmse": args.e2e_portion,
-                 "gpu": {"bulk": False, "profile": False, "device": local, "gramPath": args.gram}}
+                 "gpu": {"bulk": False, "profile": False, "device": local, "gramPath": args.gram,
+                         "cachePortions": True}}
         m2 = EmfMaster(table, opts2, rank=rank, world=world)
         m2.prepareToTrain()
         for _ in range(max(1, min(args.warmup, 2))):
@@ -311,7 +312,8 @@ def main():
             h2d, d2h = float(bb[0]), float(bb[1])
         e2e = {"value": table.nnz / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "ratings_in_portion": args.e2e_portion,
-               "api": "EmfWorker calcTrainAlsPortion/calcRmsePortion messages -> ycnr_als_portion/ycnr_rmse_portion"}
+               "api": "EmfWorker calcTrainAlsPortion/calcRmsePortion messages -> ycnr_als_portion/ycnr_rmse_portion",
+               "inputs": "converted portions cached in page-locked host memory (usePortionsCache); H2D of every portion and D2H of the solved rows inside the timed region"}
         m2.endTrain()
         del m2
 

@@ -12,6 +12,8 @@
  *                                       lib/emf/EmfBase.js:52-140
  *   ycnr_attach_factors ............... EmfBase.openSharedFactors (EmfBase.js:430-450):
  *                                       the row-major Float32 user/item matrices in SysV shm
+ *   ycnr_host_register ................ the worker's portion buffers are fixed shm segments
+ *                                       (EmfWorker.openWorkPortionBuffers, EmfWorker.js:66-89)
  *   ycnr_start_train_step ............. EmfWorker.mw_startTrainStep (EmfWorker.js:135-138)
  *   ycnr_als_portion .................. EmfWorker.mw_calcTrainAlsPortion (EmfWorker.js:169-261)
  *                                       incl. EmfBase.copySubFixedFactors (EmfBase.js:537-555),
@@ -41,6 +43,7 @@
 #ifndef YCNR_ALS_H
 #define YCNR_ALS_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -77,7 +80,10 @@ typedef struct ycnr_options {
                                    -1 = library default, 0 = never */
   int32_t split_cols;           /* ratings per partial-Gram work item for long rows; 0 = default */
   int32_t profile;              /* record CUDA events around every kernel class */
-  int32_t reserved[4];
+  int32_t tc_min_cols;          /* TC path: rows with at least this many ratings (and more than
+                                   dual_max_cols) take the tensor-core Gram; 0 = all of them */
+  int32_t tc_variant;           /* diagnostics only, keep 0 */
+  int32_t reserved[2];
 } ycnr_options;
 
 /* 'completedPortion' message fields (EmfWorker.js:254-260, 304-314) */
@@ -130,6 +136,12 @@ int ycnr_invalidate_device(ycnr_ctx* ctx, int32_t which);
 int ycnr_device_factors(ycnr_ctx* ctx, int32_t which, void** dptr_out);
 int ycnr_stream(ycnr_ctx* ctx, void** cuda_stream_out);
 int ycnr_synchronize(ycnr_ctx* ctx);
+
+/* Page-lock caller memory that holds portion buffers (the shm segments of
+ * EmfMaster.createWorkPortionBuffers, EmfMaster.js:156-234).  Portions whose indx/vals lie
+ * inside a registered region are DMA'd straight from it instead of being staged. */
+int ycnr_host_register(ycnr_ctx* ctx, void* ptr, size_t bytes);
+int ycnr_host_unregister(ycnr_ctx* ctx, void* ptr);
 
 /* ---- drop-in per-portion path (reference wire format) ------ */
 int ycnr_start_train_step(ycnr_ctx* ctx, int32_t step_type);

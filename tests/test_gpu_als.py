@@ -187,20 +187,25 @@ def test_c1_ten_iteration_trajectory(bulk):
     m.endTrain()
 
 
-def test_bulk_equals_per_portion_bitwise():
-    prob = make_problem("ml-100k", k=20, options={"ratingsInPortionForAls": {"byUser": 3000, "byItem": 3000}})
+def test_bulk_cached_and_per_portion_agree_bitwise():
+    """Three ways to feed the same step: work-buffer portions, cached page-locked portions (direct DMA),
+    device-resident row sets.  Same kernels, same rows => identical bytes, identical RMSE sums."""
+    rip = {"byUser": 3000, "byItem": 3000}
+    prob = make_problem("ml-100k", k=20, options={"ratingsInPortionForAls": rip, "ratingsInPortionForRmse": 700})
     res = []
-    for bulk in (False, True):
-        m = EmfMaster(prob["table"], {"factorsCount": 20, "seed": prob["seed"],
-                                      "ratingsInPortionForAls": {"byUser": 3000, "byItem": 3000},
-                                      "gpu": {"bulk": bulk}})
+    for gpu in ({"bulk": False}, {"bulk": False, "cachePortions": True}, {"bulk": True}):
+        m = EmfMaster(prob["table"], {"factorsCount": 20, "seed": prob["seed"], "ratingsInPortionForAls": rip,
+                                      "ratingsInPortionForRmse": 700, "gpu": gpu})
         m.prepareToTrain(prob["U0"].copy(), prob["V0"].copy())
-        m.alsTrainIter()
-        if bulk:
+        out = m.trainIter()
+        if gpu["bulk"]:
             m.syncFactorsToHost()
-        res.append((m.userFactors.copy(), m.itemFactors.copy()))
+        res.append((m.userFactors.copy(), m.itemFactors.copy(), out))
         m.endTrain()
-    assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all()
+    for other in res[1:]:
+        assert (res[0][0] == other[0]).all() and (res[0][1] == other[1]).all()
+        for key in ("rmseValidate", "rmseTest", "rmseTestShift", "globalAvgShift"):
+            assert abs(res[0][2][key] - other[2][key]) < 1e-12
 
 
 def test_c2_two_iterations_k100():

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "als_kernels.cuh"
+#include "gram_tc.cuh"
 #include "rmse_kernels.cuh"
 
 namespace {
@@ -76,7 +77,7 @@ struct WorkPlan {
   int64_t ratings_fused = 0, ratings_multi = 0;
 };
 
-void classify(const int32_t* row_len, int n_rows, int dual_max, int split_cols, WorkPlan& w) {
+void classify(const int32_t* row_len, int n_rows, int dual_max, int split_cols, int fused_max, WorkPlan& w) {
   for (int r = 0; r < n_rows; ++r) {
     const int n = row_len[r];
     if (n <= 0) continue;  // Q2 degenerate row (A = 0 upstream): skipped, see DESIGN.md
@@ -84,7 +85,7 @@ void classify(const int32_t* row_len, int n_rows, int dual_max, int split_cols, 
       const int b = (n - 1) / 16;
       w.dual[b].push_back(r);
       w.ratings_dual[b] += n;
-    } else if (n <= split_cols) {
+    } else if (n <= split_cols && n <= fused_max) {
       w.fused.push_back(r);
       w.ratings_fused += n;
     } else {
@@ -186,7 +187,13 @@ struct ycnr_ctx {
   int k = 0;
   int dual_max = 0;
   int split_cols = 0;
+  int fused_max = 0;       // rows longer than this go through the partial (+reduce) kernels
+  bool use_tc = false;     // tcgen05 3xTF32 Gram for the partial kernels
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // H2D of portion inputs, overlaps the previous portion's kernels
+  cudaEvent_t copied = nullptr;
+  std::vector<std::pair<const char*, size_t>> pinned;  // ycnr_host_register regions
   float* d_fac[2] = {nullptr, nullptr};
   float* h_fac[2] = {nullptr, nullptr};
   bool h_registered[2] = {false, false};
@@ -252,6 +259,36 @@ struct ProfScope {
 };
 
 // ---- kernel dispatch -----------------------------------------------------------------
+template <int KT>
+int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int n_items, int64_t ratings) {
+  using namespace ycnr;
+  if constexpr (4 * KT + 4 > 128) {
+    return fail("tcgen05 Gram path supports factorsCount <= 124");
+  } else {
+    GramTcArgs t{};
+    t.rows = pa.rows;
+    t.fixed = pa.fixed;
+    t.k = pa.k;
+    t.item_row = pa.item_row;
+    t.item_off = pa.item_off;
+    t.n_items = n_items;
+    t.split_cols = pa.split_cols;
+    t.partial = pa.partial;
+    t.variant = (uint32_t)c->opts.tc_variant;
+    const size_t smem = gram_tc_smem_bytes<KT>();
+    static bool configured = false;
+    if (!configured) {
+      CU(cudaFuncSetAttribute(gram_tc_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    const int grid = std::min(n_items, c->num_sms);
+    ProfScope ps(c, YCNR_K_GRAM_TC, n_items, ratings);
+    gram_tc_kernel<KT><<<grid, kTcThreads, smem, c->stream>>>(t);
+    CU(cudaGetLastError());
+    return 0;
+  }
+}
+
 template <int KT, int NT>
 int launch_primal_kt(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p, const int32_t* plan_base) {
   using namespace ycnr;
@@ -268,7 +305,9 @@ int launch_primal_kt(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p
     a.item_row = plan_base + p.off_item_row;
     a.item_off = plan_base + p.off_item_off;
     a.partial = (float*)c->partial.p;
-    {
+    if (c->use_tc) {
+      OK((launch_gram_tc<KT>(c, a, p.n_items, p.ratings_multi)));
+    } else {
       ProfScope ps(c, YCNR_K_GRAM_PARTIAL, p.n_items, p.ratings_multi);
       als_primal_kernel<KT, NT, 1, MODE_PARTIAL><<<p.n_items, NT, 0, c->stream>>>(a);
     }
@@ -413,7 +452,7 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
   s.ratings = off;
   if (R > 0) { s.first_row = ids[0]; s.last_row = ids[R - 1]; }
   WorkPlan w;
-  if (with_plan) classify(len.data(), R, c->dual_max, c->split_cols, w);
+  if (with_plan) classify(len.data(), R, c->dual_max, c->split_cols, c->fused_max, w);
   const size_t pw = with_plan ? plan_words(w) : 0;
   // layout (8-byte aligned sections): start[R] i64 | sums f64 [2R+3] | ids[R] | len[R] | pfirst[2] | plan | indx | vals
   auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
@@ -434,11 +473,20 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
     sl.pending = false;
   }
   if (!sl.done) CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
-  if (total > sl.host_cap) {
+  // ratings that already sit in page-locked caller memory are DMA'd from there
+  auto is_pinned = [&](const void* p, size_t bytes) {
+    const char* q = (const char*)p;
+    for (auto& r : c->pinned)
+      if (q >= r.first && q + bytes <= r.first + r.second) return true;
+    return false;
+  };
+  const bool direct = off > 0 && is_pinned(indx, (size_t)off * 4) && is_pinned(vals, (size_t)off * 4);
+  const size_t host_need = direct ? o_indx : total;
+  if (host_need > sl.host_cap) {
     if (sl.host) cudaFreeHost(sl.host);
     sl.host = nullptr;
     sl.host_cap = 0;
-    size_t want = total + total / 4 + 4096;
+    size_t want = host_need + host_need / 4 + 4096;
     CU(cudaMallocHost(&sl.host, want));
     sl.host_cap = want;
   }
@@ -452,13 +500,23 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
   int32_t pf[2] = {0, R};
   memcpy(h + o_pf, pf, 8);
   if (with_plan) pack_plan(w, (int32_t*)(h + o_plan), s.plan);
-  if (off) {
-    memcpy(h + o_indx, indx, (size_t)off * 4);
-    memcpy(h + o_vals, vals, (size_t)off * 4);
-  }
   char* d = (char*)sl.dev.p;
-  // the f64 scratch section is not uploaded, but it sits inside the contiguous range
-  CU(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, c->stream));
+  // (the f64 scratch section is not meaningful on the host side, but it sits inside the range)
+  if (direct) {
+    CU(cudaMemcpyAsync(d, h, o_indx, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(d + o_indx, indx, (size_t)off * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(d + o_vals, vals, (size_t)off * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  } else {
+    if (off) {
+      memcpy(h + o_indx, indx, (size_t)off * 4);
+      memcpy(h + o_vals, vals, (size_t)off * 4);
+    }
+    CU(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  CU(cudaEventRecord(c->copied, c->copy_stream));
+  CU(cudaStreamWaitEvent(c->stream, c->copied, 0));
+  // blocking with respect to the caller's buffers: they may be refilled once we return
+  if (direct) CU(cudaEventSynchronize(c->copied));
   s.view.row_start = (const int64_t*)(d + o_start);
   s.view.row_ids = (const int32_t*)(d + o_ids);
   s.view.row_len = (const int32_t*)(d + o_len);
@@ -513,7 +571,8 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   if (o->factors_count <= 0 || o->factors_count > 128)
     return fail("factorsCount %d outside the supported range 1..128", o->factors_count);
   if (o->total_users <= 0 || o->total_items <= 0) return fail("totalUsersCount/totalItemsCount must be positive");
-  if (o->gram_path == YCNR_GRAM_TC3XTF32) return fail("gram_path=TC3XTF32 is not available in this build");
+  if (o->gram_path == YCNR_GRAM_TC3XTF32 && ((o->factors_count & 3) || o->factors_count > 124))
+    return fail("gram_path=TC3XTF32 needs factorsCount %% 4 == 0 and <= 124 (got %d)", o->factors_count);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0)
@@ -531,10 +590,15 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   c->dual_max = o->dual_max_cols < 0 ? dflt_dual : std::min(96, o->dual_max_cols);
   c->split_cols = o->split_cols > 0 ? std::max(o->split_cols, ycnr::kStageRows) : 4096;
   if (c->dual_max > c->split_cols) c->dual_max = c->split_cols;
+  c->use_tc = o->gram_path == YCNR_GRAM_TC3XTF32;
+  c->fused_max = c->use_tc ? (o->tc_min_cols > 0 ? o->tc_min_cols - 1 : 0) : c->split_cols;
+  c->num_sms = prop.multiProcessorCount;
   c->fac_rows[0] = o->total_users;
   c->fac_rows[1] = o->total_items;
   CU(cudaSetDevice(o->device));
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->copied, cudaEventDisableTiming));
   for (int w = 0; w < 2; ++w) CU(cudaMalloc(&c->d_fac[w], (size_t)c->fac_rows[w] * c->k * sizeof(float)));
   *out = c;
   return 0;
@@ -543,6 +607,7 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
 int ycnr_destroy(ycnr_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->opts.device);
+  cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->stream);
   collect_profile(c);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -558,6 +623,9 @@ int ycnr_destroy(ycnr_ctx* c) {
   }
   c->partial.release();
   c->gather_tmp.release();
+  for (auto& r : c->pinned) cudaHostUnregister((void*)r.first);
+  if (c->copied) cudaEventDestroy(c->copied);
+  cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -627,6 +695,29 @@ int ycnr_synchronize(ycnr_ctx* c) {
   OK(set_device(c));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+int ycnr_host_register(ycnr_ctx* c, void* ptr, size_t bytes) {
+  if (!c || !ptr || bytes == 0) return fail("ycnr_host_register: bad argument");
+  OK(set_device(c));
+  for (auto& r : c->pinned)
+    if (r.first == (const char*)ptr) return r.second >= bytes ? 0 : fail("ycnr_host_register: region already registered with a smaller size");
+  CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  c->pinned.emplace_back((const char*)ptr, bytes);
+  return 0;
+}
+
+int ycnr_host_unregister(ycnr_ctx* c, void* ptr) {
+  if (!c || !ptr) return fail("ycnr_host_unregister: bad argument");
+  OK(set_device(c));
+  for (size_t i = 0; i < c->pinned.size(); ++i)
+    if (c->pinned[i].first == (const char*)ptr) {
+      CU(cudaStreamSynchronize(c->copy_stream));
+      CU(cudaHostUnregister(ptr));
+      c->pinned.erase(c->pinned.begin() + i);
+      return 0;
+    }
+  return fail("ycnr_host_unregister: region not registered");
 }
 
 // ---- per-portion path -----------------------------------------------------------------
@@ -821,7 +912,7 @@ int ycnr_rowset_create(ycnr_ctx* c, int32_t step_type, int32_t n_rows, const int
   std::vector<int32_t> packed;
   if (!rmse) {
     WorkPlan w;
-    classify(row_len, n_rows, c->dual_max, c->split_cols, w);
+    classify(row_len, n_rows, c->dual_max, c->split_cols, c->fused_max, w);
     packed.resize(plan_words(w) + 1);
     pack_plan(w, packed.data(), rs.dplan);
     OK(rs.plan.ensure(packed.size() * 4));

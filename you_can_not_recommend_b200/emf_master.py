@@ -134,7 +134,37 @@ class EmfMaster(EmfBase):
         mp.emit("startTrain")
         if o["gpu"]["bulk"]:
             self.prepareBulk()
+        elif o["usePortionsCache"] and o["gpu"].get("cachePortions", False):
+            self.preparePortionsCache()
         return self
+
+    def preparePortionsCache(self):
+        """usePortionsCache taken to its limit: every portion of every step stays converted in
+        page-locked host memory, so a step only hands buffers to the worker (no fetch/convert per
+        iteration; upstream keeps one portion ahead, EmfMaster.js:434-494,656-658).  A portion's
+        indx/vals are a contiguous slice of the step's fetch, so the cache is the fetch itself plus
+        one header array per portion."""
+        self.portionCache = {}
+        for step in ("byUser", "byItem", "rmseValidate", "rmseTest"):
+            csr = self._csr(step)
+            pto = np.asarray(self.portionsRowIdTo[step], np.int32)
+            rl = fe.build_rowlist(csr, pto)
+            if csr.nnz:
+                self.ctx.host_register(csr.idx)
+                self.ctx.host_register(csr.vals)
+            prefix = "rmse" if step.startswith("rmse") else "als"
+            bufs = []
+            for p in range(len(pto)):
+                r0, r1 = int(rl.portion_first[p]), int(rl.portion_first[p + 1])
+                hdr = np.empty(2 * (r1 - r0) + 1, np.int32)
+                hdr[0] = r1 - r0
+                hdr[1::2] = rl.row_ids[r0:r1]
+                hdr[2::2] = rl.row_len[r0:r1]
+                a = int(csr.ptr[0 if p == 0 else pto[p - 1]])
+                b = max(int(csr.ptr[pto[p]]), a + 1) if csr.nnz else a
+                bufs.append({prefix + "Rows": hdr, prefix + "Indx": csr.idx[a:b], prefix + "Vals": csr.vals[a:b],
+                             "fetched": int(csr.ptr[pto[p]]) - a})
+            self.portionCache[step] = bufs
 
     def prepareBulk(self):
         """Upload every step's portions once as a device-resident row set."""
@@ -185,7 +215,13 @@ class EmfMaster(EmfBase):
             pb = self.workers[0].portionBuffer
             self.completedPortions = 0
             mp.emit("startTrainStep", {"stepType": stepType})
+            cache = getattr(self, "portionCache", None)
             for p in range(lo, hi):
+                if cache is not None:
+                    cb = cache[stepType][p]
+                    self.h2d_bytes += 8 * cb["fetched"] + 4 * len(cb["alsRows"])
+                    mp.emit("calcTrainAlsPortion", {"portionNo": p, "portionBuffer": cb})
+                    continue
                 row_from = 0 if p == 0 else int(pto[p - 1])
                 # fill the worker's buffer (EmfMaster.js:571-614, 656-658)
                 fetched = fe.build_portion_into(csr, row_from, int(pto[p]), pb["alsRows"], pb["alsIndx"], pb["alsVals"])
@@ -241,7 +277,14 @@ class EmfMaster(EmfBase):
             pto = self.portionsRowIdTo[stepType]
             pb = self.workers[0].portionBuffer
             mp.emit("startCalcRmse", {"stepType": stepType, "globalAvgShift": self.globalAvgShift})
+            cache = getattr(self, "portionCache", None)
             for p in range(lo, hi):
+                if cache is not None:
+                    cb = cache[stepType][p]
+                    self.h2d_bytes += 8 * cb["fetched"] + 4 * len(cb["rmseRows"])
+                    mp.emit("calcRmsePortion", {"portionNo": p, "portionBuffer": cb})
+                    self.d2h_bytes += 24
+                    continue
                 row_from = 0 if p == 0 else int(pto[p - 1])
                 fetched = fe.build_portion_into(csr, row_from, int(pto[p]), pb["rmseRows"], pb["rmseIndx"], pb["rmseVals"])
                 self.h2d_bytes += 8 * fetched + 4 * (2 * int(pb["rmseRows"][0]) + 1)

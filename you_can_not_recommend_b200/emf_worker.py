@@ -107,7 +107,7 @@ class EmfWorker(EmfBase):
     # -- the hot path ---------------------------------------------------------------------
     def mw_calcTrainAlsPortion(self, msg):
         """EmfWorker.mw_calcTrainAlsPortion (EmfWorker.js:169-261)."""
-        pb = self.portionBuffer
+        pb = msg.get("portionBuffer") or self.portionBuffer     # cached portion (usePortionsCache) or the work buffer
         info = self.ctx.als_portion(pb["alsRows"], pb["alsIndx"], pb["alsVals"])
         self.process.emit("completedPortion", {
             "portionNo": msg["portionNo"],
@@ -119,7 +119,7 @@ class EmfWorker(EmfBase):
 
     def mw_calcRmsePortion(self, msg):
         """EmfWorker.mw_calcRmsePortion (EmfWorker.js:266-315)."""
-        pb = self.portionBuffer
+        pb = msg.get("portionBuffer") or self.portionBuffer
         info = self.ctx.rmse_portion(pb["rmseRows"], pb["rmseIndx"], pb["rmseVals"])
         self.process.emit("completedPortion", {
             "portionNo": msg["portionNo"],

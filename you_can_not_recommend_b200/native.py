@@ -21,7 +21,7 @@ KERNEL_CLASSES = ["primal_fused", "dual_fused", "gram_partial", "reduce_solve", 
 EXPORTS = [
     "ycnr_last_error", "ycnr_device_count", "ycnr_create", "ycnr_destroy", "ycnr_attach_factors",
     "ycnr_upload_factors", "ycnr_download_factors", "ycnr_invalidate_device", "ycnr_device_factors",
-    "ycnr_stream", "ycnr_synchronize", "ycnr_start_train_step", "ycnr_als_portion", "ycnr_end_train_step",
+    "ycnr_stream", "ycnr_synchronize", "ycnr_host_register", "ycnr_host_unregister", "ycnr_start_train_step", "ycnr_als_portion", "ycnr_end_train_step",
     "ycnr_start_calc_rmse", "ycnr_rmse_portion", "ycnr_s_als_build_sub_fixed_facts", "ycnr_rowset_create",
     "ycnr_rowset_destroy", "ycnr_als_rowset", "ycnr_rmse_rowset", "ycnr_ipc_export", "ycnr_ipc_import",
     "ycnr_ipc_close", "ycnr_set_peers", "ycnr_profile_reset", "ycnr_profile_read",
@@ -34,7 +34,8 @@ class Options(C.Structure):
         ("user_fact_reg", C.c_double), ("item_fact_reg", C.c_double),
         ("use_double_precision", C.c_int32), ("lowmem", C.c_int32), ("device", C.c_int32),
         ("gram_path", C.c_int32), ("dual_max_cols", C.c_int32), ("split_cols", C.c_int32),
-        ("profile", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("profile", C.c_int32), ("tc_min_cols", C.c_int32), ("tc_variant", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -93,12 +94,13 @@ class Context:
 
     def __init__(self, factors_count, total_users, total_items, user_fact_reg=0.05, item_fact_reg=0.05,
                  use_double_precision=False, lowmem=False, device=0, gram_path=GRAM_AUTO, dual_max_cols=-1,
-                 split_cols=0, profile=False):
+                 split_cols=0, profile=False, tc_min_cols=0, tc_variant=0):
         o = Options()
         o.factors_count, o.total_users, o.total_items = factors_count, total_users, total_items
         o.user_fact_reg, o.item_fact_reg = user_fact_reg, item_fact_reg
         o.use_double_precision, o.lowmem, o.device = int(use_double_precision), int(lowmem), device
         o.gram_path, o.dual_max_cols, o.split_cols, o.profile = gram_path, dual_max_cols, split_cols, int(profile)
+        o.tc_min_cols, o.tc_variant = tc_min_cols, tc_variant
         self._h = C.c_void_p()
         self.k, self.total_users, self.total_items = factors_count, total_users, total_items
         self._keep = []
@@ -139,6 +141,14 @@ class Context:
 
     def synchronize(self):
         _check(lib().ycnr_synchronize(self._h))
+
+    def host_register(self, array):
+        """Page-lock a numpy array that holds portion buffers (direct DMA instead of staging)."""
+        _check(lib().ycnr_host_register(self._h, C.c_void_p(array.ctypes.data), C.c_size_t(array.nbytes)))
+        self._keep.append(array)
+
+    def host_unregister(self, array):
+        _check(lib().ycnr_host_unregister(self._h, C.c_void_p(array.ctypes.data)))
 
     # -- per-portion path
     def start_train_step(self, step_type):
