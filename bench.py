@@ -210,7 +210,8 @@ def main():
             dist.barrier()
 
     # ---------------- device-resident iterations (value) ----------------
-    opts = {"factorsCount": k, "gpu": {"bulk": True, "profile": True, "device": local, "gramPath": args.gram}}
+    opts = {"factorsCount": k, "gpu": {"bulk": True, "profile": True, "device": local, "gramPath": args.gram,
+                                       "tcMinCols": int(os.environ.get("YCNR_TC_MIN", "0"))}}
     m = EmfMaster(table, opts, rank=rank, world=world)
     m.prepareToTrain()
     if world > 1 and args.fused_peers:

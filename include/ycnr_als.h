@@ -186,6 +186,10 @@ int ycnr_ipc_close(ycnr_ctx* ctx, void* dptr);
  * them as well (fused all-gather).  n_peers = 0 clears. Max 7 peers. */
 int ycnr_set_peers(ycnr_ctx* ctx, int32_t which, int32_t n_peers, void* const* peer_dptrs);
 
+/* ---- diagnostics ------------------------------------------------------------ */
+/* Copy the tile partials ([items][tiles][16] floats) left by the last split-row launch. */
+int ycnr_debug_read_partials(ycnr_ctx* ctx, float* out, int64_t n_floats);
+
 /* ---- measurement ------------------------------------------------------------ */
 int ycnr_profile_reset(ycnr_ctx* ctx);
 int ycnr_profile_read(ycnr_ctx* ctx, ycnr_profile* out);   /* synchronises the stream */

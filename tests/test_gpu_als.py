@@ -53,7 +53,8 @@ def test_tiny_golden_exact_rationals():
 
 @pytest.mark.parametrize("k", [20, 100, 7, 32, 50, 64, 128])
 @pytest.mark.parametrize("dual", [-1, 0])
-def test_adversarial_row_lengths_vs_oracle(k, dual):
+@pytest.mark.parametrize("gram", [native.GRAM_FFMA, native.GRAM_AUTO])
+def test_adversarial_row_lengths_vs_oracle(k, dual, gram):
     rng = np.random.default_rng(100 + k)
     n_fixed, n_solved = 3000, 64
     F = rng.normal(0, 0.3, (n_fixed, k)).astype(np.float32)
@@ -70,10 +71,10 @@ def test_adversarial_row_lengths_vs_oracle(k, dual):
     for step in (native.BY_USER, native.BY_ITEM):
         S = S0.copy()
         if step == native.BY_USER:
-            ctx = native.Context(k, n_solved, n_fixed, 0.05, 0.05, dual_max_cols=dual)
+            ctx = native.Context(k, n_solved, n_fixed, 0.05, 0.05, dual_max_cols=dual, gram_path=gram)
             ctx.attach_factors(S, F)
         else:
-            ctx = native.Context(k, n_fixed, n_solved, 0.05, 0.05, dual_max_cols=dual)
+            ctx = native.Context(k, n_fixed, n_solved, 0.05, 0.05, dual_max_cols=dual, gram_path=gram)
             ctx.attach_factors(F, S)
         info = run_portion(ctx, step, rows, indx, v)
         assert info.ratings_in_portion == sum(lens)
@@ -99,7 +100,8 @@ def test_split_rows_match_unsplit(k, split):
     out = []
     for sc in (split, 0):
         S = np.zeros((len(lens), k), np.float32)
-        ctx = native.Context(k, len(lens), n_fixed, 0.05, 0.05, split_cols=sc, profile=True)
+        ctx = native.Context(k, len(lens), n_fixed, 0.05, 0.05, split_cols=sc, profile=True,
+                             gram_path=native.GRAM_FFMA)
         ctx.attach_factors(S, F)
         run_portion(ctx, native.BY_USER, rows, indx, v)
         prof = ctx.profile_read()
@@ -109,6 +111,33 @@ def test_split_rows_match_unsplit(k, split):
         assert worst_row_rel(S, S64) < FACTOR_TOL
         out.append(S)
     assert rel_fro(out[0], out[1]) < 1e-5
+
+
+@pytest.mark.parametrize("k,split,tc_min", [(100, 4096, 0), (100, 64, 0), (100, 1000, 300), (64, 128, 0), (20, 64, 0), (124, 512, 0)])
+def test_tensor_core_gram_matches_ffma_and_oracle(k, split, tc_min):
+    """tcgen05 3xTF32 Gram (split-precision, fp32 accumulate in TMEM) vs the FFMA path and float64."""
+    rng = np.random.default_rng(9)
+    n_fixed = 7000
+    F = rng.normal(0, 0.3, (n_fixed, k)).astype(np.float32)
+    lens = [97, 128, 129, 255, 256, 257, 999, 4096, 4097, 6999]
+    ids = list(range(len(lens)))
+    cols, vals = random_rows(rng, lens, n_fixed)
+    rows, indx, v = portion_from_rows(ids, cols, vals)
+    S64 = np.zeros((len(lens), k))
+    oracle.als_portion(rows, indx, v, F.astype(np.float64), S64, 0.05)
+    out = {}
+    for name, gram in (("ffma", native.GRAM_FFMA), ("tc", native.GRAM_TC3XTF32)):
+        S = np.zeros((len(lens), k), np.float32)
+        ctx = native.Context(k, len(lens), n_fixed, 0.05, 0.05, split_cols=split, profile=True, gram_path=gram,
+                             tc_min_cols=tc_min)
+        ctx.attach_factors(S, F)
+        run_portion(ctx, native.BY_USER, rows, indx, v)
+        prof = ctx.profile_read()
+        assert (prof["gram_tc"]["launches"] > 0) == (name == "tc")
+        ctx.close()
+        assert worst_row_rel(S, S64) < FACTOR_TOL / 10, name
+        out[name] = S
+    assert worst_row_rel(out["tc"], out["ffma"]) < 1e-4
 
 
 def test_zero_cols_rows_are_skipped_and_empty_portion():

@@ -15,11 +15,13 @@
 //   symmetrised X is b.  FP32 accumulation in TMEM throughout.
 //
 // Operand layout in shared memory (both A and B are "MN-major": the reduction index — the
-// rating — is the slow index of the gathered rows):  canonical SWIZZLE_128B MN-major atoms
-// of 8 ratings x 32 factors (1024 B), byte = panel*PANEL + kgroup*1024 + (r%8)*128 +
-// ((chunk ^ (r%8)) * 16); panels 0..3 hold H (factor columns 0..127, zero padded beyond KP),
-// panels 4..7 hold 2L.  A reads M = 128 (panels 0..3), B reads N = 256 (panels 0..7) from
-// the same descriptor.
+// rating — is the slow index of the gathered rows).  For MN-major 32-bit operands the only
+// legal canonical layout is SWIZZLE_128B_BASE32B: atoms of 4 ratings x 32 factors (512 B),
+//   byte = panel*PANEL + (r/4)*512 + (r%4)*128 + ((chunk32 ^ (r%4)) * 32) + (byte % 32)
+// (Swizzle<2,5,2>: address bits [5,7) ^= bits [7,9)); LBO = PANEL (next 32 factors),
+// SBO = 512 (next 4 ratings); one K = 8 MMA consumes two atoms.  Panels 0..3 hold H (factor
+// columns 0..127, zero padded beyond KP), panels 4..7 hold 2L.  A reads M = 128 (panels
+// 0..3), B reads N = 256 (panels 0..7) from the same descriptor.
 //
 // CTA = 1 per SM (all 512 TMEM columns: two 256-column accumulators), warp-specialised:
 //   warps 0-3   epilogue: tcgen05.ld -> smem X -> symmetrise -> tile partials to HBM
@@ -50,7 +52,7 @@ struct GramTcArgs {
   int n_items;
   int split_cols;
   float* __restrict__ partial;   // [items][tiles][16]
-  uint32_t variant;              // debug: bit0 swaps LBO/SBO
+  uint32_t variant;              // diagnostics: 1 swaps LBO/SBO, 2/4 raw H^T H / H^T 2L, 8 plain SWIZZLE_128B
 };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -70,14 +72,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!ok);
 }
 
-// SWIZZLE_128B, MN-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// MN-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout);
+// layout_type 1 = SWIZZLE_128B_BASE32B, 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                 uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // start address, bits [0,14)
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset: next 32-column panel
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset: next group of 8 ratings
   d |= 1ull << 46;                                    // descriptor version (Blackwell)
-  d |= 2ull << 61;                                    // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -135,77 +139,145 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs
 
   if (warp >= 5) {
     // ============================ producers ============================
+    // Software pipeline per thread, three stages deep, so that ~2 stages of row loads per
+    // producer group (4 per SM, ~50 KB) are in flight against HBM latency:
+    //   iteration i:  load column ids of stage i+2 | issue row loads of stage i+1 | store stage i
     const int p = tid - (kTcEpiThreads + 32);
     const int group = p / kTcProdGroup;           // fills stages with (global stage index % 2) == group
     const int pt = p - group * kTcProdGroup;
     const int k = a.k;
-    uint32_t gs = 0;                              // global stage counter (all items of this CTA)
-    for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
-      const int row = a.item_row[it];
-      const int off = a.item_off[it];
-      const int64_t seg_beg = a.rows.row_start[row] + off;
-      const int seg_len = min(a.split_cols, a.rows.row_len[row] - off);
-      const int nst = (seg_len + kTcStageRows - 1) / kTcStageRows;
-      for (int st = 0; st < nst; ++st, ++gs) {
-        if ((int)(gs & 1u) != group) continue;
-        const uint32_t s = gs % kTcStages, ph = (gs / kTcStages) & 1u;
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);
-        uint8_t* sb = stage_base + s * kTcStageBytes;
-        constexpr int TASKS = kTcStageRows * NCH;
-        constexpr int PER = (TASKS + kTcProdGroup - 1) / kTcProdGroup;
-        float4 v[PER];
-        int r_[PER], q_[PER];
+    constexpr int TASKS = kTcStageRows * NCH;
+    constexpr int PER = (TASKS + kTcProdGroup - 1) / kTcProdGroup;
+    // a thread's tasks (rating row r, 16-byte chunk q of that row) are the same in every stage
+    int r_[PER], q_[PER];
+    uint32_t o_[PER];
 #pragma unroll
-        for (int u = 0; u < PER; ++u) {   // all loads of this thread first (memory-level parallelism)
-          const int task = pt + u * kTcProdGroup;
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          r_[u] = -1;
-          q_[u] = 0;
-          if (task < TASKS) {
-            const int r = task / NCH, q = task - r * NCH;
-            r_[u] = r;
-            q_[u] = q;
-            const int e = st * kTcStageRows + r;
-            if (e < seg_len) {
-              if (q < KT) {
-                if (4 * q < k) {
-                  const int col = __ldg(a.rows.indx + seg_beg + e);
-                  v[u] = __ldg(reinterpret_cast<const float4*>(a.fixed + (size_t)col * k + 4 * q));
-                }
-              } else {
-                v[u].x = __ldg(a.rows.vals + seg_beg + e);
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < PER; ++u) {
-          if (r_[u] < 0) continue;
-          const int r = r_[u], q = q_[u];
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v[u].x) & 0xFFFFE000u);
-          h.y = __uint_as_float(__float_as_uint(v[u].y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(v[u].z) & 0xFFFFE000u);
-          h.w = __uint_as_float(__float_as_uint(v[u].w) & 0xFFFFE000u);
-          l.x = __uint_as_float(__float_as_uint(2.0f * (v[u].x - h.x)) & 0xFFFFE000u);
-          l.y = __uint_as_float(__float_as_uint(2.0f * (v[u].y - h.y)) & 0xFFFFE000u);
-          l.z = __uint_as_float(__float_as_uint(2.0f * (v[u].z - h.z)) & 0xFFFFE000u);
-          l.w = __uint_as_float(__float_as_uint(2.0f * (v[u].w - h.w)) & 0xFFFFE000u);
+    for (int u = 0; u < PER; ++u) {
+      const int task = pt + u * kTcProdGroup;
+      r_[u] = -1;
+      q_[u] = 0;
+      o_[u] = 0;
+      if (task < TASKS) {
+        const int r = task / NCH, q = task - r * NCH;
+        r_[u] = r;
+        q_[u] = q;
+        if (a.variant & 8u) {   // diagnostics: plain SWIZZLE_128B atoms (8 ratings x 128 B, 16-byte chunks)
           const int r8 = r & 7;
-          const uint32_t o = (uint32_t)(q >> 3) * kTcPanelBytes + (uint32_t)(r >> 3) * 1024u + (uint32_t)r8 * 128u +
-                             (uint32_t)(((q & 7) ^ r8) << 4);
-          *reinterpret_cast<float4*>(sb + o) = h;
-          *reinterpret_cast<float4*>(sb + o + 4 * kTcPanelBytes) = l;
+          o_[u] = (uint32_t)(q >> 3) * kTcPanelBytes + (uint32_t)(r >> 3) * 1024u + (uint32_t)r8 * 128u +
+                  (uint32_t)(((q & 7) ^ r8) << 4);
+        } else {                // SWIZZLE_128B_BASE32B atoms (4 ratings x 128 B, 32-byte chunks)
+          const int r4 = r & 3;
+          o_[u] = (uint32_t)(q >> 3) * kTcPanelBytes + (uint32_t)(r >> 2) * 512u + (uint32_t)r4 * 128u +
+                  (uint32_t)(((((q & 7) >> 1) ^ r4) << 5) | ((q & 1) << 4));
         }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        mbar_arrive(full0 + 8 * s);
+      }
+    }
+    // iterator over the stages this group fills: (item, stage in item, global stage index)
+    struct StageIt {
+      int it, st, nst, seg_len;
+      int64_t seg_beg;
+      uint32_t gs;
+      bool valid;
+    };
+    auto load_item = [&](StageIt& x) {
+      if (x.it < a.n_items) {
+        const int row = a.item_row[x.it];
+        const int off = a.item_off[x.it];
+        x.seg_beg = a.rows.row_start[row] + off;
+        x.seg_len = min(a.split_cols, a.rows.row_len[row] - off);
+        x.nst = (x.seg_len + kTcStageRows - 1) / kTcStageRows;
+      }
+    };
+    auto step = [&](StageIt& x) {   // advance by one global stage
+      ++x.st;
+      ++x.gs;
+      while (x.it < a.n_items && x.st >= x.nst) {
+        x.it += gridDim.x;
+        x.st = 0;
+        load_item(x);
+      }
+      x.valid = x.it < a.n_items;
+    };
+    auto next_mine = [&](StageIt& x) {   // advance to the next stage of this group
+      do { step(x); } while (x.valid && (int)(x.gs & 1u) != group);
+    };
+    auto load_idx = [&](const StageIt& x, int (&col)[PER]) {
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        col[u] = -1;
+        if (x.valid && r_[u] >= 0 && q_[u] < KT) {
+          const int e = x.st * kTcStageRows + r_[u];
+          if (e < x.seg_len) col[u] = __ldg(a.rows.indx + x.seg_beg + e);
+        }
+      }
+    };
+    auto load_rows = [&](const StageIt& x, const int (&col)[PER], float4 (&v)[PER]) {
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!x.valid || r_[u] < 0) continue;
+        if (q_[u] < KT) {
+          if (col[u] >= 0 && 4 * q_[u] < k)
+            v[u] = __ldg(reinterpret_cast<const float4*>(a.fixed + (size_t)col[u] * k + 4 * q_[u]));
+        } else {
+          const int e = x.st * kTcStageRows + r_[u];
+          if (e < x.seg_len) v[u].x = __ldg(a.rows.vals + x.seg_beg + e);
+        }
+      }
+    };
+    StageIt A;
+    A.it = blockIdx.x; A.st = -1; A.nst = 0; A.seg_len = 0; A.seg_beg = 0; A.gs = 0xFFFFFFFFu; A.valid = true;
+    load_item(A);
+    if (A.it >= a.n_items) A.nst = 0;
+    next_mine(A);                 // first stage of this group (gs wraps to 0 on the first step)
+    StageIt B = A;
+    next_mine(B);
+    StageIt Cn = B;
+    next_mine(Cn);
+    int colA[PER], colB[PER], colC[PER];
+    float4 vA[PER], vB[PER];
+    load_idx(A, colA);
+    load_idx(B, colB);
+    load_rows(A, colA, vA);
+    while (A.valid) {
+      load_idx(Cn, colC);
+      load_rows(B, colB, vB);
+      const uint32_t s = A.gs % kTcStages, ph = (A.gs / kTcStages) & 1u;
+      mbar_wait(empty0 + 8 * s, ph ^ 1u);
+      uint8_t* sb = stage_base + s * kTcStageBytes;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        if (r_[u] < 0) continue;
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(vA[u].x) & 0xFFFFE000u);
+        h.y = __uint_as_float(__float_as_uint(vA[u].y) & 0xFFFFE000u);
+        h.z = __uint_as_float(__float_as_uint(vA[u].z) & 0xFFFFE000u);
+        h.w = __uint_as_float(__float_as_uint(vA[u].w) & 0xFFFFE000u);
+        l.x = __uint_as_float(__float_as_uint(2.0f * (vA[u].x - h.x)) & 0xFFFFE000u);
+        l.y = __uint_as_float(__float_as_uint(2.0f * (vA[u].y - h.y)) & 0xFFFFE000u);
+        l.z = __uint_as_float(__float_as_uint(2.0f * (vA[u].z - h.z)) & 0xFFFFE000u);
+        l.w = __uint_as_float(__float_as_uint(2.0f * (vA[u].w - h.w)) & 0xFFFFE000u);
+        *reinterpret_cast<float4*>(sb + o_[u]) = h;
+        *reinterpret_cast<float4*>(sb + o_[u] + 4 * kTcPanelBytes) = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      mbar_arrive(full0 + 8 * s);
+      A = B;
+      B = Cn;
+      next_mine(Cn);
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        vA[u] = vB[u];
+        colB[u] = colC[u];
       }
     }
   } else if (warp == 4) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
-      const uint32_t lbo = (a.variant & 1u) ? 1024u : (uint32_t)kTcPanelBytes;
-      const uint32_t sbo = (a.variant & 1u) ? (uint32_t)kTcPanelBytes : 1024u;
+      const uint32_t ltype = (a.variant & 8u) ? 2u : 1u;
+      const uint32_t kstride = (a.variant & 8u) ? 1024u : 512u;
+      const uint32_t lbo = (a.variant & 1u) ? kstride : (uint32_t)kTcPanelBytes;
+      const uint32_t sbo = (a.variant & 1u) ? (uint32_t)kTcPanelBytes : kstride;
       uint32_t gs = 0, itc = 0;
       for (int it = blockIdx.x; it < a.n_items; it += gridDim.x, ++itc) {
         const int row = a.item_row[it];
@@ -224,7 +296,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs
           const int ng = (rows_here + 7) >> 3;
           const uint32_t sa = smem_u32(stage_base + s * kTcStageBytes);
           for (int g = 0; g < ng; ++g) {
-            const uint64_t desc = tc_smem_desc(sa + (uint32_t)g * 1024u, lbo, sbo);
+            const uint64_t desc = tc_smem_desc(sa + (uint32_t)g * 1024u, lbo, sbo, ltype);
             const uint32_t acc = (st > 0 || g > 0) ? 1u : 0u;
             asm volatile(
                 "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
@@ -267,9 +339,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs
             : "r"(taddr + 128u + (uint32_t)c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
         if (m < NC) {
+          const bool use_h = !(a.variant & 4u), use_l = !(a.variant & 2u);   // diagnostics: raw halves
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < NC) Xs[m * kTcXsPitch + c0 + j] = __uint_as_float(h[j]) + __uint_as_float(l[j]);
+            if (c0 + j < NC)
+              Xs[m * kTcXsPitch + c0 + j] =
+                  (use_h ? __uint_as_float(h[j]) : 0.f) + (use_l ? __uint_as_float(l[j]) : 0.f);
         }
       }
       // accumulator drained: hand it back to the MMA warp before the slower smem -> HBM part
@@ -288,6 +363,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs
           o.y = 0.5f * (Xs[ri * kTcXsPitch + 4 * L + 1] + Xs[(4 * L + 1) * kTcXsPitch + ri]);
           o.z = 0.5f * (Xs[ri * kTcXsPitch + 4 * L + 2] + Xs[(4 * L + 2) * kTcXsPitch + ri]);
           o.w = 0.5f * (Xs[ri * kTcXsPitch + 4 * L + 3] + Xs[(4 * L + 3) * kTcXsPitch + ri]);
+          if (a.variant & 6u) {   // diagnostics: unsymmetrised X[4I+i][4L+j]
+            o.x = Xs[ri * kTcXsPitch + 4 * L + 0];
+            o.y = Xs[ri * kTcXsPitch + 4 * L + 1];
+            o.z = Xs[ri * kTcXsPitch + 4 * L + 2];
+            o.w = Xs[ri * kTcXsPitch + 4 * L + 3];
+          }
           *reinterpret_cast<float4*>(out + (size_t)t * 16 + 4 * i) = o;
         }
       }

@@ -590,7 +590,9 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   c->dual_max = o->dual_max_cols < 0 ? dflt_dual : std::min(96, o->dual_max_cols);
   c->split_cols = o->split_cols > 0 ? std::max(o->split_cols, ycnr::kStageRows) : 4096;
   if (c->dual_max > c->split_cols) c->dual_max = c->split_cols;
-  c->use_tc = o->gram_path == YCNR_GRAM_TC3XTF32;
+  // AUTO: tensor cores whenever the rhs column fits the M = 128 accumulator and rows are 16-byte aligned
+  c->use_tc = o->gram_path == YCNR_GRAM_TC3XTF32 ||
+              (o->gram_path == YCNR_GRAM_AUTO && (c->k & 3) == 0 && c->k <= 124 && c->k >= 16);
   c->fused_max = c->use_tc ? (o->tc_min_cols > 0 ? o->tc_min_cols - 1 : 0) : c->split_cols;
   c->num_sms = prop.multiProcessorCount;
   c->fac_rows[0] = o->total_users;
@@ -1008,6 +1010,16 @@ int ycnr_set_peers(ycnr_ctx* c, int32_t which, int32_t n, void* const* ptrs) {
   OK(set_device(c));
   CU(cudaStreamSynchronize(c->stream));
   c->peers[which].assign(ptrs, ptrs + n);
+  return 0;
+}
+
+// ---- diagnostics -----------------------------------------------------------------------------
+int ycnr_debug_read_partials(ycnr_ctx* c, float* out, int64_t n_floats) {
+  if (!c || !out || n_floats < 0) return fail("ycnr_debug_read_partials: bad argument");
+  OK(set_device(c));
+  if ((size_t)n_floats * sizeof(float) > c->partial.cap) return fail("ycnr_debug_read_partials: only %zu bytes of partials exist", c->partial.cap);
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(out, c->partial.p, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "ycnr_stream", "ycnr_synchronize", "ycnr_host_register", "ycnr_host_unregister", "ycnr_start_train_step", "ycnr_als_portion", "ycnr_end_train_step",
     "ycnr_start_calc_rmse", "ycnr_rmse_portion", "ycnr_s_als_build_sub_fixed_facts", "ycnr_rowset_create",
     "ycnr_rowset_destroy", "ycnr_als_rowset", "ycnr_rmse_rowset", "ycnr_ipc_export", "ycnr_ipc_import",
-    "ycnr_ipc_close", "ycnr_set_peers", "ycnr_profile_reset", "ycnr_profile_read",
+    "ycnr_ipc_close", "ycnr_set_peers", "ycnr_debug_read_partials", "ycnr_profile_reset", "ycnr_profile_read",
 ]
 
 
@@ -216,6 +216,11 @@ class Context:
     def set_peers(self, which, ptrs):
         arr = (C.c_void_p * max(1, len(ptrs)))(*ptrs)
         _check(lib().ycnr_set_peers(self._h, C.c_int32(which), C.c_int32(len(ptrs)), arr))
+
+    def debug_read_partials(self, n_items, n_tiles):
+        out = np.zeros((n_items, n_tiles, 4, 4), np.float32)
+        _check(lib().ycnr_debug_read_partials(self._h, _f32(out), C.c_int64(out.size)))
+        return out
 
     # -- measurement
     def profile_reset(self):
