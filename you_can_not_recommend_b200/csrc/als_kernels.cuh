@@ -44,27 +44,32 @@ __device__ __forceinline__ void tile_coords(int t, int mt, int ntri, int& I, int
   }
 }
 
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // MUFU.RSQ, <= 2 ulp; no IEEE sqrt/div chains
+  return y;
+}
+
 // Cholesky of a symmetric 4x4 tile held in full; on return d holds M = L^-1 (lower
-// triangle, zeros above).  sqrtf and the divisions are IEEE (no fast-math).
+// triangle, zeros above).  Only reciprocal square roots are needed: L's diagonal never
+// appears on its own.  This is the serial link of every factorisation step, so it uses the
+// MUFU approximation (relative error 2^-22, the same order as one fp32 rounding) instead of
+// IEEE sqrtf + division (~4x the latency).
 __device__ __forceinline__ void chol4_inverse(float (&d)[4][4]) {
-  const float l00 = sqrtf(d[0][0]);
-  const float i0 = 1.0f / l00;
+  const float i0 = rsqrt_fast(d[0][0]);
   const float l10 = d[1][0] * i0, l20 = d[2][0] * i0, l30 = d[3][0] * i0;
-  const float l11 = sqrtf(d[1][1] - l10 * l10);
-  const float i1 = 1.0f / l11;
-  const float l21 = (d[2][1] - l20 * l10) * i1;
-  const float l31 = (d[3][1] - l30 * l10) * i1;
-  const float l22 = sqrtf(d[2][2] - l20 * l20 - l21 * l21);
-  const float i2 = 1.0f / l22;
-  const float l32 = (d[3][2] - l30 * l20 - l31 * l21) * i2;
-  const float l33 = sqrtf(d[3][3] - l30 * l30 - l31 * l31 - l32 * l32);
-  const float i3 = 1.0f / l33;
+  const float i1 = rsqrt_fast(fmaf(-l10, l10, d[1][1]));
+  const float l21 = fmaf(-l20, l10, d[2][1]) * i1;
+  const float l31 = fmaf(-l30, l10, d[3][1]) * i1;
+  const float i2 = rsqrt_fast(fmaf(-l21, l21, fmaf(-l20, l20, d[2][2])));
+  const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, d[3][2])) * i2;
+  const float i3 = rsqrt_fast(fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, d[3][3]))));
   const float m10 = -(l10 * i0) * i1;
   const float m21 = -(l21 * i1) * i2;
   const float m32 = -(l32 * i2) * i3;
-  const float m20 = -(l20 * i0 + l21 * m10) * i2;
-  const float m31 = -(l31 * i1 + l32 * m21) * i3;
-  const float m30 = -(l30 * i0 + l31 * m10 + l32 * m20) * i3;
+  const float m20 = -fmaf(l21, m10, l20 * i0) * i2;
+  const float m31 = -fmaf(l32, m21, l31 * i1) * i3;
+  const float m30 = -fmaf(l32, m20, fmaf(l31, m10, l30 * i0)) * i3;
   d[0][0] = i0;  d[0][1] = 0.f; d[0][2] = 0.f; d[0][3] = 0.f;
   d[1][0] = m10; d[1][1] = i1;  d[1][2] = 0.f; d[1][3] = 0.f;
   d[2][0] = m20; d[2][1] = m21; d[2][2] = i2;  d[2][3] = 0.f;
@@ -73,32 +78,37 @@ __device__ __forceinline__ void chol4_inverse(float (&d)[4][4]) {
 
 // Blocked right-looking Cholesky + both triangular solves on register tiles.
 //   acc[q]  : tile (tI[q], tL[q]) of the bordered system; tI = tL = -1 marks "no tile".
-//   panel   : (mt+1)*16 floats, dinv: 16 floats, ysm: 4*mt floats of shared memory.
+//   panel   : (mt+1)*16 floats ([4][mt+1] float4), minv: mt*16 floats (inverse of every diagonal factor tile),
+//             ysm: 4*mt floats of shared memory.
 // On return ysm[0 .. 4*mt) holds the solution.  All threads of the CTA must call.
+// Two barriers per tile column in the factorisation (the owner of the next diagonal tile
+// factors it right after its own trailing update — look-ahead — so nobody waits on a
+// dedicated "factor" phase) and one per tile row in the back substitution.
 template <int TPT>
 __device__ __forceinline__ void tile_cholesky_solve(float (&acc)[TPT][4][4], const int (&tI)[TPT],
-                                                    const int (&tL)[TPT], int mt, float* panel, float* dinv,
+                                                    const int (&tL)[TPT], int mt, float* panel, float* minv,
                                                     float* ysm) {
+  auto factor_and_publish = [&](float (&t)[4][4], float* dst) {
+    chol4_inverse(t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(t[i][0], t[i][1], t[i][2], t[i][3]);
+  };
+  const int ps = mt + 1;   // panel is laid out [i][I]: lanes owning consecutive tiles read consecutive 16-byte units
+#pragma unroll
+  for (int q = 0; q < TPT; ++q)
+    if (tI[q] == 0 && tL[q] == 0) factor_and_publish(acc[q], minv);
+  __syncthreads();
   for (int J = 0; J < mt; ++J) {
-    // (a) factor the diagonal tile, publish M = L_JJ^-1
-#pragma unroll
-    for (int q = 0; q < TPT; ++q) {
-      if (tI[q] == J && tL[q] == J) {
-        chol4_inverse(acc[q]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<float4*>(dinv + 4 * i) = make_float4(acc[q][i][0], acc[q][i][1], acc[q][i][2], acc[q][i][3]);
-      }
-    }
-    __syncthreads();
-    // (b) panel: X_IJ = A_IJ * L_JJ^-T  (rows I > J, including the rhs row I = mt)
+    const float* dcur = minv + 16 * J;
+    // (a) panel: X_IJ = A_IJ * L_JJ^-T  (rows I > J, including the rhs row I = mt)
 #pragma unroll
     for (int q = 0; q < TPT; ++q) {
       if (tL[q] == J && tI[q] > J) {
         float m[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 v = *reinterpret_cast<const float4*>(dinv + 4 * i);
+          const float4 v = *reinterpret_cast<const float4*>(dcur + 4 * i);
           m[i][0] = v.x; m[i][1] = v.y; m[i][2] = v.z; m[i][3] = v.w;
         }
 #pragma unroll
@@ -109,21 +119,22 @@ __device__ __forceinline__ void tile_cholesky_solve(float (&acc)[TPT][4][4], con
           const float x2 = fmaf(a2, m[2][2], fmaf(a1, m[2][1], a0 * m[2][0]));
           const float x3 = fmaf(a3, m[3][3], fmaf(a2, m[3][2], fmaf(a1, m[3][1], a0 * m[3][0])));
           acc[q][i][0] = x0; acc[q][i][1] = x1; acc[q][i][2] = x2; acc[q][i][3] = x3;
-          *reinterpret_cast<float4*>(panel + 16 * tI[q] + 4 * i) = make_float4(x0, x1, x2, x3);
+          *reinterpret_cast<float4*>(panel + 4 * (i * ps + tI[q])) = make_float4(x0, x1, x2, x3);
         }
       }
     }
     __syncthreads();
-    // (c) trailing update: A_IL -= X_IJ * X_LJ^T for J < L <= I
+    // (b) trailing update: A_IL -= X_IJ * X_LJ^T for J < L <= I; the owner of the next
+    //     diagonal tile then factors it and publishes its inverse for step J + 1
 #pragma unroll
     for (int q = 0; q < TPT; ++q) {
       if (tL[q] > J) {
         float xi[4][4], xl[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 v = *reinterpret_cast<const float4*>(panel + 16 * tI[q] + 4 * i);
+          const float4 v = *reinterpret_cast<const float4*>(panel + 4 * (i * ps + tI[q]));
           xi[i][0] = v.x; xi[i][1] = v.y; xi[i][2] = v.z; xi[i][3] = v.w;
-          const float4 w = *reinterpret_cast<const float4*>(panel + 16 * tL[q] + 4 * i);
+          const float4 w = *reinterpret_cast<const float4*>(panel + 4 * (i * ps + tL[q]));
           xl[i][0] = w.x; xl[i][1] = w.y; xl[i][2] = w.z; xl[i][3] = w.w;
         }
 #pragma unroll
@@ -135,32 +146,36 @@ __device__ __forceinline__ void tile_cholesky_solve(float (&acc)[TPT][4][4], con
             for (int c = 0; c < 4; ++c) s = fmaf(-xi[i][c], xl[j][c], s);
             acc[q][i][j] = s;
           }
-      }
-    }
-    // the next (a) only touches the owner's own registers and dinv, whose readers all
-    // passed the barrier after (b); panel is rewritten only after the barrier after (a).
-  }
-  // y = L^-1 b sits in row 0 of the rhs tiles
-#pragma unroll
-  for (int q = 0; q < TPT; ++q) {
-    if (tI[q] == mt && tL[q] >= 0)
-      *reinterpret_cast<float4*>(ysm + 4 * tL[q]) = make_float4(acc[q][0][0], acc[q][0][1], acc[q][0][2], acc[q][0][3]);
-  }
-  __syncthreads();
-  // back substitution L^T x = y, right-looking over tile rows
-  for (int I = mt - 1; I >= 0; --I) {
-#pragma unroll
-    for (int q = 0; q < TPT; ++q) {
-      if (tI[q] == I && tL[q] == I) {  // acc holds M = L_II^-1 ; x_I = M^T y_I
-        const float4 y = *reinterpret_cast<const float4*>(ysm + 4 * I);
-        const float x0 = fmaf(acc[q][3][0], y.w, fmaf(acc[q][2][0], y.z, fmaf(acc[q][1][0], y.y, acc[q][0][0] * y.x)));
-        const float x1 = fmaf(acc[q][3][1], y.w, fmaf(acc[q][2][1], y.z, acc[q][1][1] * y.y));
-        const float x2 = fmaf(acc[q][3][2], y.w, acc[q][2][2] * y.z);
-        const float x3 = acc[q][3][3] * y.w;
-        *reinterpret_cast<float4*>(ysm + 4 * I) = make_float4(x0, x1, x2, x3);
+        if (tL[q] == J + 1 && tI[q] == J + 1) factor_and_publish(acc[q], minv + 16 * (J + 1));
       }
     }
     __syncthreads();
+    // panel is rewritten in (a) of the next step: all its readers passed the barrier above
+  }
+  // y = L^-1 b sits in row 0 of the rhs tiles; x_I = M_I^T y_I finishes block row I
+  auto apply_minv_t = [&](int I, float4 y) {
+    const float* m = minv + 16 * I;
+    const float4 r0 = *reinterpret_cast<const float4*>(m), r1 = *reinterpret_cast<const float4*>(m + 4);
+    const float4 r2 = *reinterpret_cast<const float4*>(m + 8), r3 = *reinterpret_cast<const float4*>(m + 12);
+    float4 x;
+    x.x = fmaf(r3.x, y.w, fmaf(r2.x, y.z, fmaf(r1.x, y.y, r0.x * y.x)));
+    x.y = fmaf(r3.y, y.w, fmaf(r2.y, y.z, r1.y * y.y));
+    x.z = fmaf(r3.z, y.w, r2.z * y.z);
+    x.w = r3.w * y.w;
+    return x;
+  };
+#pragma unroll
+  for (int q = 0; q < TPT; ++q) {
+    if (tI[q] == mt && tL[q] >= 0) {
+      float4 y = make_float4(acc[q][0][0], acc[q][0][1], acc[q][0][2], acc[q][0][3]);
+      if (tL[q] == mt - 1) y = apply_minv_t(mt - 1, y);
+      *reinterpret_cast<float4*>(ysm + 4 * tL[q]) = y;
+    }
+  }
+  __syncthreads();
+  // back substitution L^T x = y, right-looking over tile rows: in round I the tiles (I, L<I)
+  // push x_I into y_L; the tile (I, I-1) makes the last contribution to y_{I-1} and turns it into x_{I-1}
+  for (int I = mt - 1; I > 0; --I) {
 #pragma unroll
     for (int q = 0; q < TPT; ++q) {
       if (tI[q] == I && tL[q] >= 0 && tL[q] < I) {  // y_L -= X_IL^T x_I
@@ -170,6 +185,7 @@ __device__ __forceinline__ void tile_cholesky_solve(float (&acc)[TPT][4][4], con
         y.y -= acc[q][0][1] * x.x + acc[q][1][1] * x.y + acc[q][2][1] * x.z + acc[q][3][1] * x.w;
         y.z -= acc[q][0][2] * x.x + acc[q][1][2] * x.y + acc[q][2][2] * x.z + acc[q][3][2] * x.w;
         y.w -= acc[q][0][3] * x.x + acc[q][1][3] * x.y + acc[q][2][3] * x.z + acc[q][3][3] * x.w;
+        if (tL[q] == I - 1) y = apply_minv_t(I - 1, y);
         *reinterpret_cast<float4*>(ysm + 4 * tL[q]) = y;
       }
     }
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(NT) als_primal_kernel(const PrimalArgs a) {
   static_assert(NT * TPT >= NTILES, "not enough threads for the tile set");
   __shared__ __align__(16) float Ys[(MODE == MODE_REDUCE) ? 1 : 2 * kStageRows * PITCH];
   __shared__ __align__(16) float panel[(KT + 1) * 16];
-  __shared__ __align__(16) float dinv[16];
+  __shared__ __align__(16) float minv[KT * 16];
   __shared__ __align__(16) float ysm[KP];
 
   const int tid = threadIdx.x;
@@ -352,7 +368,7 @@ __global__ void __launch_bounds__(NT) als_primal_kernel(const PrimalArgs a) {
       }
     }
   }
-  tile_cholesky_solve<TPT>(acc, tI, tL, KT, panel, dinv, ysm);
+  tile_cholesky_solve<TPT>(acc, tI, tL, KT, panel, minv, ysm);
 
   const int rowId = a.rows.row_ids[row];
   for (int c = tid; c < k; c += NT) {
@@ -381,8 +397,8 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
   extern __shared__ __align__(16) float dsm[];
   float* Y = dsm;                              // [NMAX][pitch]
   float* panel = Y + NMAX * a.pitch;           // (MT_MAX+1)*16
-  float* dinv = panel + (MT_MAX + 1) * 16;     // 16
-  float* ysm = dinv + 16;                      // NMAX
+  float* minv = panel + (MT_MAX + 1) * 16;     // MT_MAX x 16
+  float* ysm = minv + MT_MAX * 16;             // NMAX
   float* vs = ysm + NMAX;                      // NMAX
 
   const int tid = threadIdx.x;
@@ -395,20 +411,23 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
   const int np = 4 * mt;
 
   // ---- gather the n rated rows of F -----------------------------------------------
+  // Rating r (= row 4I+i of the system) is staged in slot i*mt + I: the four rows of a tile
+  // sit mt slots apart, so lanes owning consecutive tiles read consecutive slots and the
+  // LDS.128 of the Gram loop are bank-conflict free (pitch/4 is odd).
   if ((k & 3) == 0) {
     const int CH = k >> 2;
     for (int q = tid; q < np * CH; q += NT) {
       const int r = q / CH, c = q - r * CH;
       const bool ok = r < n;
       const int col = ok ? __ldg(a.rows.indx + beg + r) : 0;
-      cp_async16(Y + r * pitch + 4 * c, a.fixed + (size_t)col * k + 4 * c, ok ? 16 : 0);
+      cp_async16(Y + ((r & 3) * mt + (r >> 2)) * pitch + 4 * c, a.fixed + (size_t)col * k + 4 * c, ok ? 16 : 0);
     }
   } else {
     for (int q = tid; q < np * K4; q += NT) {
       const int r = q / K4, c = q - r * K4;
       const bool ok = r < n && c < k;
       const int col = ok ? __ldg(a.rows.indx + beg + r) : 0;
-      cp_async4(Y + r * pitch + c, a.fixed + (size_t)col * k + (ok ? c : 0), ok ? 4 : 0);
+      cp_async4(Y + ((r & 3) * mt + (r >> 2)) * pitch + c, a.fixed + (size_t)col * k + (ok ? c : 0), ok ? 4 : 0);
     }
   }
   for (int r = tid; r < np; r += NT) vs[r] = r < n ? __ldg(a.rows.vals + beg + r) : 0.f;
@@ -428,14 +447,15 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
     for (int j = 0; j < 4; ++j) acc[0][i][j] = 0.f;
 
   if (tI[0] >= 0 && tI[0] < mt) {
-    const float* ya = Y + 4 * tI[0] * pitch;
-    const float* yb = Y + 4 * tL[0] * pitch;
+    const float* ya = Y + tI[0] * pitch;
+    const float* yb = Y + tL[0] * pitch;
+    const int tstride = mt * pitch;
     for (int c = 0; c < K4; c += 4) {
       float4 av[4], bv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        av[i] = *reinterpret_cast<const float4*>(ya + i * pitch + c);
-        bv[i] = *reinterpret_cast<const float4*>(yb + i * pitch + c);
+        av[i] = *reinterpret_cast<const float4*>(ya + i * tstride + c);
+        bv[i] = *reinterpret_cast<const float4*>(yb + i * tstride + c);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -461,13 +481,22 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
     const float4 v = *reinterpret_cast<const float4*>(vs + 4 * tL[0]);
     acc[0][0][0] = v.x; acc[0][0][1] = v.y; acc[0][0][2] = v.z; acc[0][0][3] = v.w;
   }
-  tile_cholesky_solve<1>(acc, tI, tL, mt, panel, dinv, ysm);
+  tile_cholesky_solve<1>(acc, tI, tL, mt, panel, minv, ysm);
 
   // ---- x = Y^T z --------------------------------------------------------------------------
   const int rowId = a.rows.row_ids[row];
+  for (int p = tid; p < np; p += NT) vs[(p & 3) * mt + (p >> 2)] = ysm[p];   // z in slot order (pad rows: z = 0)
+  __syncthreads();
   for (int c = tid; c < k; c += NT) {
-    float x = 0.f;
-    for (int p = 0; p < n; ++p) x = fmaf(Y[p * pitch + c], ysm[p], x);
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+    const float* yc = Y + c;
+    for (int s = 0; s < np; s += 4) {   // four independent chains; np is a multiple of 4
+      x0 = fmaf(yc[(s + 0) * pitch], vs[s + 0], x0);
+      x1 = fmaf(yc[(s + 1) * pitch], vs[s + 1], x1);
+      x2 = fmaf(yc[(s + 2) * pitch], vs[s + 2], x2);
+      x3 = fmaf(yc[(s + 3) * pitch], vs[s + 3], x3);
+    }
+    const float x = (x0 + x1) + (x2 + x3);
     for (int d = 0; d < a.dst.n; ++d) a.dst.p[d][(size_t)rowId * k + c] = x;
   }
 }

@@ -41,7 +41,6 @@ constexpr int kTcStageBytes = 8 * kTcPanelBytes;              // 4 H panels + 4 
 constexpr int kTcEpiThreads = 128;
 constexpr int kTcProdGroup = 256;                             // threads per producer group
 constexpr int kTcThreads = kTcEpiThreads + 32 + 2 * kTcProdGroup;  // 672
-constexpr int kTcXsPitch = 109;                               // odd: conflict-free row-per-thread stores
 
 struct GramTcArgs {
   RowsView rows;
@@ -97,7 +96,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs
   constexpr int NTRI = KT * (KT + 1) / 2;
   constexpr int NTILES = NTRI + KT;
   static_assert(KP + 4 <= 128, "rhs column must fit the M = 128 accumulator");
-  static_assert(NC <= kTcXsPitch, "X pitch too small");
+  constexpr int kTcXsPitch = NC | 1;   // odd: conflict-free row-per-thread stores
 
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   // carve: [stages][32 KB] | Xs[NC][pitch] | barriers | tmem base
@@ -386,7 +385,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs
 
 template <int KT>
 constexpr size_t gram_tc_smem_bytes() {
-  return (size_t)kTcStages * kTcStageBytes + (size_t)128 * kTcXsPitch * sizeof(float) + (2 * kTcStages + 4) * 8 + 16 +
+  return (size_t)kTcStages * kTcStageBytes + (size_t)128 * ((4 * KT + 4) | 1) * sizeof(float) + (2 * kTcStages + 4) * 8 + 16 +
          1024 /* alignment slack */;
 }
 

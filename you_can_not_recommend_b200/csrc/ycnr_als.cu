@@ -329,6 +329,7 @@ int launch_primal(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p, c
   if (k <= 32) return launch_primal_kt<8, 64>(c, base, p, plan_base);
   if (k <= 64) return launch_primal_kt<16, 160>(c, base, p, plan_base);
   if (k <= 100) return launch_primal_kt<25, 352>(c, base, p, plan_base);
+  if (k <= 124) return launch_primal_kt<31, 544>(c, base, p, plan_base);  // largest KT whose rhs column fits M = 128
   if (k <= 128) return launch_primal_kt<32, 576>(c, base, p, plan_base);
   return fail("factorsCount %d > 128 is not supported by this build", k);
 }
@@ -339,7 +340,7 @@ int launch_dual_bin(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t 
   if (count <= 0) return 0;
   DualArgs a = base;
   a.work = work;
-  const size_t smem = ((size_t)4 * MT_MAX * a.pitch + (MT_MAX + 1) * 16 + 16 + 8 * MT_MAX) * sizeof(float);
+  const size_t smem = ((size_t)4 * MT_MAX * a.pitch + (MT_MAX + 1) * 16 + 16 * MT_MAX + 8 * MT_MAX) * sizeof(float);
   static size_t configured = 0;  // per instantiation
   if (smem > 48 * 1024 && smem > configured) {
     CU(cudaFuncSetAttribute(als_dual_kernel<MT_MAX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
