@@ -82,7 +82,7 @@ typedef struct ycnr_options {
   int32_t profile;              /* record CUDA events around every kernel class */
   int32_t tc_min_cols;          /* TC path: rows with at least this many ratings (and more than
                                    dual_max_cols) take the tensor-core Gram; 0 = all of them */
-  int32_t tc_variant;           /* diagnostics only, keep 0 */
+  int32_t tc_variant;           /* diagnostics only, keep 0 (16: raw fp32 in the TF32 head columns) */
   int32_t reserved[2];
 } ycnr_options;
 

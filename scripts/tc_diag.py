@@ -19,7 +19,7 @@ for r, n in enumerate(lens):
     ref[r] = np.linalg.solve(Y.T @ Y + 0.05 * n * np.eye(k), Y.T @ np.asarray(vals[r]))
 for name, kw in (("ffma", dict(gram_path=native.GRAM_FFMA)),
                  ("tc v0", dict(gram_path=native.GRAM_TC3XTF32, tc_variant=0)),
-                 ("tc v1", dict(gram_path=native.GRAM_TC3XTF32, tc_variant=1))):
+                 ("tc raw-head", dict(gram_path=native.GRAM_TC3XTF32, tc_variant=16))):
     S = np.zeros((len(lens), k), np.float32)
     try:
         ctx = native.Context(k, len(lens), n_fixed, 0.05, 0.05, profile=True, **kw)

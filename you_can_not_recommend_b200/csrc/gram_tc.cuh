@@ -6,28 +6,39 @@
 //
 // Split-precision scheme (error-compensated TF32, "3xTF32" with the symmetric halves merged):
 //   every fp32 element y is split into  h = tf32(y)  (low 13 mantissa bits cleared) and
-//   l = y - h.  One MMA per 8 ratings computes
-//       D[128 x 256] += H^T [ H | 2L ]           (M = 128, N = 256, K = 8, kind::tf32)
-//   i.e. columns 0..127 accumulate H^T H and columns 128..255 accumulate H^T (2L).  With
-//   X = D[:, :128] + D[:, 128:], the symmetrised (X + X^T)/2 = H^T H + H^T L + L^T H, the
+//   l = y - h (exact).  One MMA per 8 ratings computes
+//       D[128 x 2*NC] += H^T [ H | L ]          (M = 128, N = 2*NC, K = 8, kind::tf32)
+//   i.e. columns 0..NC-1 accumulate H^T H and columns NC..2NC-1 accumulate H^T L.  With
+//   X = D[:, :NC] + 2 D[:, NC:], the symmetrised (X + X^T)/2 = H^T H + H^T L + L^T H, the
 //   three significant terms of (H+L)^T (H+L); only L^T L (~2^-22 relative) is dropped.
 //   The ratings r ride along as one extra operand column (index KP): row/column KP of the
-//   symmetrised X is b.  FP32 accumulation in TMEM throughout.
+//   symmetrised X is b.  FP32 accumulation in TMEM throughout.  NC = KP + 4 rounded up to 8,
+//   so the MMA is exactly as wide as the system needs (N = 208 at k = 100, not 256).
 //
 // Operand layout in shared memory (both A and B are "MN-major": the reduction index — the
-// rating — is the slow index of the gathered rows).  For MN-major 32-bit operands the only
-// legal canonical layout is SWIZZLE_128B_BASE32B: atoms of 4 ratings x 32 factors (512 B),
-//   byte = panel*PANEL + (r/4)*512 + (r%4)*128 + ((chunk32 ^ (r%4)) * 32) + (byte % 32)
-// (Swizzle<2,5,2>: address bits [5,7) ^= bits [7,9)); LBO = PANEL (next 32 factors),
-// SBO = 512 (next 4 ratings); one K = 8 MMA consumes two atoms.  Panels 0..3 hold H (factor
-// columns 0..127, zero padded beyond KP), panels 4..7 hold 2L.  A reads M = 128 (panels
-// 0..3), B reads N = 256 (panels 0..7) from the same descriptor.
+// rating — is the slow index of the gathered rows).  For MN-major 32-bit operands the
+// canonical layout is SWIZZLE_128B_BASE32B: atoms of 4 ratings x 32 columns (512 B),
+//   byte = panel*4096 + (r/4)*512 + (r%4)*128 + ((chunk32 ^ (r%4)) * 32) + (byte % 32)
+// LBO = 4096 (next 32 columns), SBO = 512 (next 4 ratings); one K = 8 MMA consumes two atoms.
+// A stage holds 32 ratings x NPAN panels: columns [0, NC) = H, [NC, 2NC) = L.  A reads
+// M = 128 columns and B reads N = 2*NC columns from the same descriptor.
+//
+// Data movement: the gathered factor rows go HBM/L2 -> shared memory with 16-byte cp.async
+// straight into their swizzled H position (no register staging); a loader warp requests the
+// column ids of its next stage before it issues the current one.  The H columns keep the raw fp32 bits: kind::tf32 ignores
+// the low 13 mantissa bits of its operands (verified bit-for-bit on B200 against explicitly
+// masked operands), so only the tail l = y - tf32(y) has to be produced by CUDA cores:
+// one LDS, one STS and 8 ALU ops per 16 bytes.
 //
 // CTA = 1 per SM (all 512 TMEM columns: two 256-column accumulators), warp-specialised:
-//   warps 0-3   epilogue: tcgen05.ld -> smem X -> symmetrise -> tile partials to HBM
-//   warp  4     TMEM alloc + single-thread MMA issue (tcgen05.mma / tcgen05.commit)
-//   warps 5-20  producers: indexed gather (LDG.128) -> split -> swizzled STS, two groups of
-//               8 warps filling alternate stages of a 5-deep mbarrier ring
+//   warps 0-3    epilogue: tcgen05.ld -> smem X -> symmetrise -> tile partials to HBM
+//   warp  4      TMEM alloc + single-thread MMA issue (tcgen05.mma / tcgen05.commit)
+//   next STAGES warps  loaders: warp w owns ring slot w; one cp.async instruction moves one rating
+//                (lane = 16-byte chunk), column ids are broadcast by shuffle.  Completion is
+//                signalled per stage with cp.async.mbarrier.arrive; loaders never execute a
+//                fence, so up to STAGES stages of copies stay in flight against HBM latency
+//   next STAGES warps  splitters: warp w owns ring slot w: tail columns, fence.proxy.async, hand
+//                the stage to the MMA warp
 #pragma once
 #include "als_kernels.cuh"
 #include "common.cuh"
@@ -35,12 +46,32 @@
 namespace ycnr {
 
 constexpr int kTcStageRows = 32;                              // ratings per stage (4 MMAs of K = 8)
-constexpr int kTcStages = 5;
 constexpr int kTcPanelBytes = (kTcStageRows / 8) * 1024;      // one 32-column panel of one stage
-constexpr int kTcStageBytes = 8 * kTcPanelBytes;              // 4 H panels + 4 2L panels = 32 KB
 constexpr int kTcEpiThreads = 128;
-constexpr int kTcProdGroup = 256;                             // threads per producer group
-constexpr int kTcThreads = kTcEpiThreads + 32 + 2 * kTcProdGroup;  // 672
+// One loader warp and one splitter warp per ring slot: a warp sees every use of "its" slot in
+// order, which is what makes waiting on an mbarrier phase PARITY sound (a warp that hopped between
+// slots could be two phases off and sail through a wait).
+constexpr int kTcSmemLimit = 232448;                          // 227 KB per CTA on sm_100
+
+template <int KT>
+struct TcCfg {
+  static constexpr int KP = 4 * KT;            // padded system size; the ratings column sits at index KP
+  static constexpr int NCH = KT + 1;           // 16-byte chunks per rating: KT data chunks + (val,0,0,0)
+  static constexpr int NC = (KP + 4 + 7) & ~7; // columns of H (and of L) seen by the MMA
+  static constexpr int N = 2 * NC;             // MMA N
+  static constexpr int NPAN = (N + 31) / 32 < 4 ? 4 : (N + 31) / 32;   // A reads 4 panels (M = 128)
+  static constexpr int STAGE_BYTES = NPAN * kTcPanelBytes;
+  static constexpr int XP = NC | 1;            // odd pitch: conflict-free row-per-thread stores
+  static constexpr int XS_BYTES = (NC * XP * 4 + 15) & ~15;
+  static constexpr int STAGES_FIT = (kTcSmemLimit - 2048 - XS_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT < 6 ? STAGES_FIT : 6;
+  static constexpr int THREADS = kTcEpiThreads + 32 + 2 * 32 * STAGES;   // epilogue | MMA | loaders | splitters
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + XS_BYTES + (3 * STAGES + 4) * 8 + 16 + 1024;
+  static_assert(KP + 4 <= 128, "rhs column must fit the M = 128 accumulator");
+  static_assert(NCH <= 32, "one lane per 16-byte chunk of a rating");
+  static_assert(N <= 256 && N % 16 == 0, "MMA N");
+  static_assert(STAGES >= 4, "not enough shared memory for the stage ring");
+};
 
 struct GramTcArgs {
   RowsView rows;
@@ -51,7 +82,7 @@ struct GramTcArgs {
   int n_items;
   int split_cols;
   float* __restrict__ partial;   // [items][tiles][16]
-  uint32_t variant;              // diagnostics: 1 swaps LBO/SBO, 2/4 raw H^T H / H^T 2L, 8 plain SWIZZLE_128B
+  uint32_t variant;              // diagnostics: 16 = splitters also overwrite the H columns with explicitly masked values
 };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -72,52 +103,104 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // MN-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout);
-// layout_type 1 = SWIZZLE_128B_BASE32B, 2 = SWIZZLE_128B
+// layout_type 1 = SWIZZLE_128B_BASE32B
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                  uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // start address, bits [0,14)
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset: next 32-column panel
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset: next group of 8 ratings
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset: next group of 4 ratings
   d |= 1ull << 46;                                    // descriptor version (Blackwell)
   d |= (uint64_t)layout_type << 61;
   return d;
 }
 
-// kind::tf32, fp32 accumulate, A and B MN-major, M = 128, N = 256 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((256u >> 3) << 17) |
-                              ((128u >> 4) << 24);
+// byte offset of the 16-byte chunk that starts at column c (multiple of 4) of rating r inside a stage
+__device__ __forceinline__ uint32_t tc_chunk_offset(int r, int c) {
+  return (uint32_t)(c >> 5) * kTcPanelBytes + (uint32_t)(r >> 2) * 512u + (uint32_t)(r & 3) * 128u +
+         (uint32_t)(((((c & 31) >> 3) ^ (r & 3)) << 5) | (((c >> 2) & 1) << 4));
+}
+
+// Walks the CTA's work items stage by stage (items blockIdx.x, +gridDim.x, ...; the host never
+// emits an empty slice).  Every thread of a role walks it redundantly: the descriptor loads are
+// warp-uniform and cache-resident, and the descriptor of the following item is requested one
+// item early so its latency is off the critical path.
+struct TcItemIter {
+  int it, st, nst, seg_len;
+  int64_t seg_beg;
+  int n_seg_len;
+  int64_t n_seg_beg;
+  __device__ __forceinline__ void fetch(const GramTcArgs& a, int item, int64_t& beg, int& len) {
+    beg = 0;
+    len = 0;
+    if (item < a.n_items) {
+      const int row = __ldg(a.item_row + item);
+      const int off = __ldg(a.item_off + item);
+      beg = __ldg(a.rows.row_start + row) + off;
+      len = max(0, min(a.split_cols, __ldg(a.rows.row_len + row) - off));
+    }
+  }
+  __device__ __forceinline__ void init(const GramTcArgs& a) {
+    it = blockIdx.x;
+    st = 0;
+    fetch(a, it, seg_beg, seg_len);
+    nst = (seg_len + kTcStageRows - 1) / kTcStageRows;
+    fetch(a, it + gridDim.x, n_seg_beg, n_seg_len);
+  }
+  __device__ __forceinline__ bool valid(const GramTcArgs& a) const { return it < a.n_items; }
+  __device__ __forceinline__ void next_item(const GramTcArgs& a) {
+    it += gridDim.x;
+    st = 0;
+    seg_beg = n_seg_beg;
+    seg_len = n_seg_len;
+    nst = (seg_len + kTcStageRows - 1) / kTcStageRows;
+    fetch(a, it + gridDim.x, n_seg_beg, n_seg_len);
+  }
+  __device__ __forceinline__ void next(const GramTcArgs& a) {
+    if (++st >= nst) next_item(a);
+  }
+  __device__ __forceinline__ void advance(const GramTcArgs& a, int stages) {
+    st += stages;
+    while (it < a.n_items && st >= nst) {
+      const int over = st - nst;
+      next_item(a);
+      st = over;
+    }
+  }
+};
 
 template <int KT>
-__global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs a) {
-  constexpr int KP = 4 * KT;           // padded system size; the ratings column sits at index KP
-  constexpr int NCH = KT + 1;          // 16-byte chunks written per rating: KT data chunks + (val,0,0,0)
-  constexpr int NC = KP + 4;           // rows/columns of X that are consumed
+__global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const GramTcArgs a) {
+  using Cfg = TcCfg<KT>;
+  constexpr int NCH = Cfg::NCH, NC = Cfg::NC, XP = Cfg::XP;
+  constexpr int STAGES = Cfg::STAGES;
   constexpr int NTRI = KT * (KT + 1) / 2;
   constexpr int NTILES = NTRI + KT;
-  static_assert(KP + 4 <= 128, "rhs column must fit the M = 128 accumulator");
-  constexpr int kTcXsPitch = NC | 1;   // odd: conflict-free row-per-thread stores
+  // kind::tf32, fp32 accumulate, A and B MN-major, M = 128, N = 2*NC (cute::UMMA::InstrDescriptor)
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(Cfg::N >> 3) << 17) | ((128u >> 4) << 24);
 
   extern __shared__ __align__(1024) uint8_t tc_smem[];
-  // carve: [stages][32 KB] | Xs[NC][pitch] | barriers | tmem base
+  // carve: [stages][STAGE_BYTES] | Xs[NC][XP] | barriers | tmem base
   // SWIZZLE_128B atoms are addressed by absolute shared-memory bits [7,10): align the ring to 1024 B
   uint8_t* stage_base = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
-  float* Xs = reinterpret_cast<float*>(stage_base + kTcStages * kTcStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Xs + 128 * kTcXsPitch);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 4);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kTcStages);
-  const uint32_t accf0 = smem_u32(bars + 2 * kTcStages), acce0 = smem_u32(bars + 2 * kTcStages + 2);
+  float* Xs = reinterpret_cast<float*>(stage_base + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + STAGES * Cfg::STAGE_BYTES + Cfg::XS_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), raw0 = smem_u32(bars + 2 * STAGES);
+  const uint32_t accf0 = smem_u32(bars + 3 * STAGES), acce0 = smem_u32(bars + 3 * STAGES + 2);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
-  // zero every stage once: pad chunks (>= NCH) are never written again
-  for (int i = tid; i < kTcStages * kTcStageBytes / 16; i += kTcThreads)
+  // zero every stage once: pad columns are never written again
+  for (int i = tid; i < STAGES * Cfg::STAGE_BYTES / 16; i += Cfg::THREADS)
     reinterpret_cast<float4*>(stage_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
-    for (int s = 0; s < kTcStages; ++s) {
-      mbar_init(full0 + 8 * s, kTcProdGroup);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
+      mbar_init(raw0 + 8 * s, 32);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf0 + 8 * b, 1);
@@ -137,170 +220,133 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 5) {
-    // ============================ producers ============================
-    // Software pipeline per thread, three stages deep, so that ~2 stages of row loads per
-    // producer group (4 per SM, ~50 KB) are in flight against HBM latency:
-    //   iteration i:  load column ids of stage i+2 | issue row loads of stage i+1 | store stage i
-    const int p = tid - (kTcEpiThreads + 32);
-    const int group = p / kTcProdGroup;           // fills stages with (global stage index % 2) == group
-    const int pt = p - group * kTcProdGroup;
+    const bool loader = warp < 5 + STAGES;
     const int k = a.k;
-    constexpr int TASKS = kTcStageRows * NCH;
-    constexpr int PER = (TASKS + kTcProdGroup - 1) / kTcProdGroup;
-    // a thread's tasks (rating row r, 16-byte chunk q of that row) are the same in every stage
-    int r_[PER], q_[PER];
-    uint32_t o_[PER];
+    // lane = 16-byte chunk of a rating (lanes 0..KT-1: factors, lane KT: the rating value).
+    // Offsets of that chunk for the four values of r % 4 (the swizzle phase); + (r / 4) * 512.
+    uint32_t oh4[4], ol4[4];
 #pragma unroll
-    for (int u = 0; u < PER; ++u) {
-      const int task = pt + u * kTcProdGroup;
-      r_[u] = -1;
-      q_[u] = 0;
-      o_[u] = 0;
-      if (task < TASKS) {
-        const int r = task / NCH, q = task - r * NCH;
-        r_[u] = r;
-        q_[u] = q;
-        if (a.variant & 8u) {   // diagnostics: plain SWIZZLE_128B atoms (8 ratings x 128 B, 16-byte chunks)
-          const int r8 = r & 7;
-          o_[u] = (uint32_t)(q >> 3) * kTcPanelBytes + (uint32_t)(r >> 3) * 1024u + (uint32_t)r8 * 128u +
-                  (uint32_t)(((q & 7) ^ r8) << 4);
-        } else {                // SWIZZLE_128B_BASE32B atoms (4 ratings x 128 B, 32-byte chunks)
-          const int r4 = r & 3;
-          o_[u] = (uint32_t)(q >> 3) * kTcPanelBytes + (uint32_t)(r >> 2) * 512u + (uint32_t)r4 * 128u +
-                  (uint32_t)(((((q & 7) >> 1) ^ r4) << 5) | ((q & 1) << 4));
-        }
-      }
+    for (int j = 0; j < 4; ++j) {
+      oh4[j] = tc_chunk_offset(j, 4 * min(lane, NCH - 1));
+      ol4[j] = tc_chunk_offset(j, NC + 4 * min(lane, NCH - 1));
     }
-    // iterator over the stages this group fills: (item, stage in item, global stage index)
-    struct StageIt {
-      int it, st, nst, seg_len;
-      int64_t seg_beg;
-      uint32_t gs;
-      bool valid;
-    };
-    auto load_item = [&](StageIt& x) {
-      if (x.it < a.n_items) {
-        const int row = a.item_row[x.it];
-        const int off = a.item_off[x.it];
-        x.seg_beg = a.rows.row_start[row] + off;
-        x.seg_len = min(a.split_cols, a.rows.row_len[row] - off);
-        x.nst = (x.seg_len + kTcStageRows - 1) / kTcStageRows;
-      }
-    };
-    auto step = [&](StageIt& x) {   // advance by one global stage
-      ++x.st;
-      ++x.gs;
-      while (x.it < a.n_items && x.st >= x.nst) {
-        x.it += gridDim.x;
-        x.st = 0;
-        load_item(x);
-      }
-      x.valid = x.it < a.n_items;
-    };
-    auto next_mine = [&](StageIt& x) {   // advance to the next stage of this group
-      do { step(x); } while (x.valid && (int)(x.gs & 1u) != group);
-    };
-    auto load_idx = [&](const StageIt& x, int (&col)[PER]) {
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        col[u] = -1;
-        if (x.valid && r_[u] >= 0 && q_[u] < KT) {
-          const int e = x.st * kTcStageRows + r_[u];
-          if (e < x.seg_len) col[u] = __ldg(a.rows.indx + x.seg_beg + e);
+    TcItemIter ix;
+    ix.init(a);
+    if (loader) {
+      // ============================ loaders ============================
+      constexpr int W = STAGES;
+      const int w = warp - 5;
+      ix.advance(a, w);
+      uint32_t g = (uint32_t)w;
+      // lane r: column id and position of rating r of the stage under the iterator
+      auto load_ids = [&](const TcItemIter& x, int& col, uint32_t& vm, int64_t& e0) {
+        col = 0;
+        e0 = 0;
+        bool ok = false;
+        if (x.valid(a)) {
+          e0 = x.seg_beg + (int64_t)x.st * kTcStageRows;
+          ok = x.st * kTcStageRows + lane < x.seg_len;
+          if (ok) col = __ldg(a.rows.indx + e0 + lane);
         }
-      }
-    };
-    auto load_rows = [&](const StageIt& x, const int (&col)[PER], float4 (&v)[PER]) {
+        vm = __ballot_sync(0xffffffffu, ok);
+      };
+      auto issue = [&](uint32_t gg, int col, uint32_t vm, int64_t e0) {
+        const uint32_t s = gg % STAGES, ph = (gg / STAGES) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        uint8_t* sb = stage_base + s * Cfg::STAGE_BYTES;
+        const float* src_lane = a.fixed + 4 * lane;
+        const bool lane_ok = lane < KT && 4 * lane < k;
 #pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!x.valid || r_[u] < 0) continue;
-        if (q_[u] < KT) {
-          if (col[u] >= 0 && 4 * q_[u] < k)
-            v[u] = __ldg(reinterpret_cast<const float4*>(a.fixed + (size_t)col[u] * k + 4 * q_[u]));
-        } else {
-          const int e = x.st * kTcStageRows + r_[u];
-          if (e < x.seg_len) v[u].x = __ldg(a.rows.vals + x.seg_beg + e);
+        for (int r = 0; r < kTcStageRows; ++r) {
+          const int c = __shfl_sync(0xffffffffu, col, r);
+          const bool ok = ((vm >> r) & 1u) && lane_ok;
+          if (lane < KT) cp_async16(sb + oh4[r & 3] + (r >> 2) * 512, src_lane + (size_t)c * k, ok ? 16 : 0);
         }
+        {   // the 32 rating values of the stage: lane r -> column KP of rating r, (val, 0, 0, 0)
+          const bool ok = (vm >> lane) & 1u;
+          cp_async4(sb + tc_chunk_offset(lane, 4 * KT), a.rows.vals + (ok ? e0 + lane : 0), ok ? 4 : 0);
+        }
+        // this lane's arrival on the stage's raw barrier fires when its copies have landed
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(raw0 + 8 * s) : "memory");
+      };
+      // two register sets (A/B): the ids of the warp's next stage are requested before the current
+      // stage is issued and are never moved while the load is outstanding
+      int colA, colB;
+      uint32_t vmA, vmB;
+      int64_t eA, eB;
+      load_ids(ix, colA, vmA, eA);
+      while (ix.valid(a)) {
+        ix.advance(a, W);
+        load_ids(ix, colB, vmB, eB);
+        issue(g, colA, vmA, eA);
+        g += W;
+        if (!ix.valid(a)) break;
+        ix.advance(a, W);
+        load_ids(ix, colA, vmA, eA);
+        issue(g, colB, vmB, eB);
+        g += W;
       }
-    };
-    StageIt A;
-    A.it = blockIdx.x; A.st = -1; A.nst = 0; A.seg_len = 0; A.seg_beg = 0; A.gs = 0xFFFFFFFFu; A.valid = true;
-    load_item(A);
-    if (A.it >= a.n_items) A.nst = 0;
-    next_mine(A);                 // first stage of this group (gs wraps to 0 on the first step)
-    StageIt B = A;
-    next_mine(B);
-    StageIt Cn = B;
-    next_mine(Cn);
-    int colA[PER], colB[PER], colC[PER];
-    float4 vA[PER], vB[PER];
-    load_idx(A, colA);
-    load_idx(B, colB);
-    load_rows(A, colA, vA);
-    while (A.valid) {
-      load_idx(Cn, colC);
-      load_rows(B, colB, vB);
-      const uint32_t s = A.gs % kTcStages, ph = (A.gs / kTcStages) & 1u;
-      mbar_wait(empty0 + 8 * s, ph ^ 1u);
-      uint8_t* sb = stage_base + s * kTcStageBytes;
+      cp_async_wait<0>();
+    } else {
+      // ============================ splitters ============================
+      constexpr int W = STAGES;
+      const int w = warp - 5 - STAGES;
+      const bool mask_head = (a.variant & 16u) != 0;
+      ix.advance(a, w);
+      for (uint32_t g = (uint32_t)w; ix.valid(a); g += W, ix.advance(a, W)) {
+        const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
+        mbar_wait(raw0 + 8 * s, ph);
+        uint8_t* sb = stage_base + s * Cfg::STAGE_BYTES;
+        if (lane < NCH) {
 #pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        if (r_[u] < 0) continue;
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(vA[u].x) & 0xFFFFE000u);
-        h.y = __uint_as_float(__float_as_uint(vA[u].y) & 0xFFFFE000u);
-        h.z = __uint_as_float(__float_as_uint(vA[u].z) & 0xFFFFE000u);
-        h.w = __uint_as_float(__float_as_uint(vA[u].w) & 0xFFFFE000u);
-        l.x = __uint_as_float(__float_as_uint(2.0f * (vA[u].x - h.x)) & 0xFFFFE000u);
-        l.y = __uint_as_float(__float_as_uint(2.0f * (vA[u].y - h.y)) & 0xFFFFE000u);
-        l.z = __uint_as_float(__float_as_uint(2.0f * (vA[u].z - h.z)) & 0xFFFFE000u);
-        l.w = __uint_as_float(__float_as_uint(2.0f * (vA[u].w - h.w)) & 0xFFFFE000u);
-        *reinterpret_cast<float4*>(sb + o_[u]) = h;
-        *reinterpret_cast<float4*>(sb + o_[u] + 4 * kTcPanelBytes) = l;
-      }
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      mbar_arrive(full0 + 8 * s);
-      A = B;
-      B = Cn;
-      next_mine(Cn);
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        vA[u] = vB[u];
-        colB[u] = colC[u];
+          for (int r = 0; r < kTcStageRows; ++r) {
+            uint8_t* ph_ = sb + oh4[r & 3] + (r >> 2) * 512;
+            const float4 v = *reinterpret_cast<const float4*>(ph_);
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            l.x = v.x - h.x;
+            l.y = v.y - h.y;
+            l.z = v.z - h.z;
+            l.w = v.w - h.w;
+            if (mask_head) *reinterpret_cast<float4*>(ph_) = h;
+            *reinterpret_cast<float4*>(sb + ol4[r & 3] + (r >> 2) * 512) = l;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full0 + 8 * s);
       }
     }
   } else if (warp == 4) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
-      const uint32_t ltype = (a.variant & 8u) ? 2u : 1u;
-      const uint32_t kstride = (a.variant & 8u) ? 1024u : 512u;
-      const uint32_t lbo = (a.variant & 1u) ? kstride : (uint32_t)kTcPanelBytes;
-      const uint32_t sbo = (a.variant & 1u) ? (uint32_t)kTcPanelBytes : kstride;
+      TcItemIter ix;
+      ix.init(a);
       uint32_t gs = 0, itc = 0;
-      for (int it = blockIdx.x; it < a.n_items; it += gridDim.x, ++itc) {
-        const int row = a.item_row[it];
-        const int off = a.item_off[it];
-        const int seg_len = min(a.split_cols, a.rows.row_len[row] - off);
-        const int nst = (seg_len + kTcStageRows - 1) / kTcStageRows;
+      while (ix.valid(a)) {
+        const int nst = ix.nst, seg_len = ix.seg_len;
         const uint32_t buf = itc & 1u, aph = (itc >> 1) & 1u;
+        ++itc;
         mbar_wait(acce0 + 8 * buf, aph ^ 1u);       // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint32_t d_tmem = tmem_base + buf * 256u;
         for (int st = 0; st < nst; ++st, ++gs) {
-          const uint32_t s = gs % kTcStages, ph = (gs / kTcStages) & 1u;
+          const uint32_t s = gs % STAGES, ph = (gs / STAGES) & 1u;
           mbar_wait(full0 + 8 * s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const int rows_here = min(kTcStageRows, seg_len - st * kTcStageRows);
           const int ng = (rows_here + 7) >> 3;
-          const uint32_t sa = smem_u32(stage_base + s * kTcStageBytes);
+          const uint32_t sa = smem_u32(stage_base + s * Cfg::STAGE_BYTES);
           for (int g = 0; g < ng; ++g) {
-            const uint64_t desc = tc_smem_desc(sa + (uint32_t)g * 1024u, lbo, sbo, ltype);
+            const uint64_t desc = tc_smem_desc(sa + (uint32_t)g * 1024u, kTcPanelBytes, 512u, 1u);
             const uint32_t acc = (st > 0 || g > 0) ? 1u : 0u;
             asm volatile(
                 "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
                 " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-                "l"(desc), "l"(desc), "r"(kTcIdesc), "r"(acc)
+                "l"(desc), "l"(desc), "r"(IDESC), "r"(acc)
                 : "memory");
           }
           // frees the stage for the producers once the MMAs above have read it
@@ -311,6 +357,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
                          accf0 + 8 * buf)
                      : "memory");
+        ix.next_item(a);
       }
     }
     __syncwarp();
@@ -318,8 +365,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs
     // ============================ epilogue ============================
     const int m = tid;  // TMEM lane == row of X; warp w may only touch lanes 32w .. 32w+31
     uint32_t itc = 0;
-    for (int it = blockIdx.x; it < a.n_items; it += gridDim.x, ++itc) {
+    for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
       const uint32_t buf = itc & 1u, aph = (itc >> 1) & 1u;
+      ++itc;
       mbar_wait(accf0 + 8 * buf, aph);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16) + buf * 256u;
@@ -335,15 +383,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
             : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]), "=r"(l[4]), "=r"(l[5]), "=r"(l[6]), "=r"(l[7]),
               "=r"(l[8]), "=r"(l[9]), "=r"(l[10]), "=r"(l[11]), "=r"(l[12]), "=r"(l[13]), "=r"(l[14]), "=r"(l[15])
-            : "r"(taddr + 128u + (uint32_t)c0));
+            : "r"(taddr + (uint32_t)NC + (uint32_t)c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
         if (m < NC) {
-          const bool use_h = !(a.variant & 4u), use_l = !(a.variant & 2u);   // diagnostics: raw halves
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < NC)
-              Xs[m * kTcXsPitch + c0 + j] =
-                  (use_h ? __uint_as_float(h[j]) : 0.f) + (use_l ? __uint_as_float(l[j]) : 0.f);
+            if (c0 + j < NC) Xs[m * XP + c0 + j] = fmaf(2.0f, __uint_as_float(l[j]), __uint_as_float(h[j]));
         }
       }
       // accumulator drained: hand it back to the MMA warp before the slower smem -> HBM part
@@ -358,16 +403,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs
         for (int i = 0; i < 4; ++i) {
           float4 o;
           const int ri = 4 * I + i;
-          o.x = 0.5f * (Xs[ri * kTcXsPitch + 4 * L + 0] + Xs[(4 * L + 0) * kTcXsPitch + ri]);
-          o.y = 0.5f * (Xs[ri * kTcXsPitch + 4 * L + 1] + Xs[(4 * L + 1) * kTcXsPitch + ri]);
-          o.z = 0.5f * (Xs[ri * kTcXsPitch + 4 * L + 2] + Xs[(4 * L + 2) * kTcXsPitch + ri]);
-          o.w = 0.5f * (Xs[ri * kTcXsPitch + 4 * L + 3] + Xs[(4 * L + 3) * kTcXsPitch + ri]);
-          if (a.variant & 6u) {   // diagnostics: unsymmetrised X[4I+i][4L+j]
-            o.x = Xs[ri * kTcXsPitch + 4 * L + 0];
-            o.y = Xs[ri * kTcXsPitch + 4 * L + 1];
-            o.z = Xs[ri * kTcXsPitch + 4 * L + 2];
-            o.w = Xs[ri * kTcXsPitch + 4 * L + 3];
-          }
+          o.x = 0.5f * (Xs[ri * XP + 4 * L + 0] + Xs[(4 * L + 0) * XP + ri]);
+          o.y = 0.5f * (Xs[ri * XP + 4 * L + 1] + Xs[(4 * L + 1) * XP + ri]);
+          o.z = 0.5f * (Xs[ri * XP + 4 * L + 2] + Xs[(4 * L + 2) * XP + ri]);
+          o.w = 0.5f * (Xs[ri * XP + 4 * L + 3] + Xs[(4 * L + 3) * XP + ri]);
           *reinterpret_cast<float4*>(out + (size_t)t * 16 + 4 * i) = o;
         }
       }
@@ -385,8 +424,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gram_tc_kernel(const GramTcArgs
 
 template <int KT>
 constexpr size_t gram_tc_smem_bytes() {
-  return (size_t)kTcStages * kTcStageBytes + (size_t)128 * ((4 * KT + 4) | 1) * sizeof(float) + (2 * kTcStages + 4) * 8 + 16 +
-         1024 /* alignment slack */;
+  return TcCfg<KT>::SMEM;
 }
 
 }  // namespace ycnr

@@ -283,7 +283,7 @@ int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int n_items, int64_t
     }
     const int grid = std::min(n_items, c->num_sms);
     ProfScope ps(c, YCNR_K_GRAM_TC, n_items, ratings);
-    gram_tc_kernel<KT><<<grid, kTcThreads, smem, c->stream>>>(t);
+    gram_tc_kernel<KT><<<grid, TcCfg<KT>::THREADS, smem, c->stream>>>(t);
     CU(cudaGetLastError());
     return 0;
   }
