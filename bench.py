@@ -101,6 +101,19 @@ def measured_peaks():
         return 6650.0, "fallback"
 
 
+def measured_traffic(workload, k, cls):
+    """DRAM bytes per launch of kernel class `cls` from the committed ncu --set full capture
+    (profiles/traffic_<workload>.json, written by scripts/gpu_round1_final.sh + DESIGN.md §5); None when
+    there is no capture for this workload / rank."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_%s.json" % workload)))
+        if k != 100:
+            return None
+        return float(t[cls]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def build_table(args):
     from you_can_not_recommend_b200 import front_end as fe
     t = fe.synth_table(args.workload)
@@ -267,7 +280,9 @@ def main():
         alg_flops = ratings_per_launch * k * k                  # F_gram = nnz * k^2 (symmetric-aware)
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                "frac": achieved / peak, "traffic": measured_traffic(args.workload, k, dom) if world == 1 else None,
+                "traffic_source": "profiles/traffic_%s.json (ncu --set full, dram read+write per launch)" % args.workload,
+                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
                 "launch_ms": per_launch_ms, "launches_timed": prof[dom]["launches"],
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "gram_tflops": alg_flops / (per_launch_ms * 1e-3) / 1e12,

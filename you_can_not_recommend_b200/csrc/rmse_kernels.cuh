@@ -37,35 +37,65 @@ __global__ void __launch_bounds__(256) rmse_rows_kernel(const RmseArgs a) {
   const float* uf = a.U + (size_t)u * k;
   const int grp = lane >> 3, gl = lane & 7;
   double sd2 = 0.0, sp = 0.0;
-  const bool vec = (k & 3) == 0;
-  for (int j0 = 0; j0 < n; j0 += 4) {     // uniform trip count for the whole warp
-    const int j = j0 + grp;
-    const bool ok = j < n;
-    float dot = 0.f;
-    if (ok) {
-      const int it = __ldg(a.rows.indx + beg + j);
-      const float* vf = a.V + (size_t)it * k;
-      if (vec) {
-        for (int c = gl * 4; c < k; c += 32) {
-          const float4 x = __ldg(reinterpret_cast<const float4*>(uf + c));
-          const float4 y = __ldg(reinterpret_cast<const float4*>(vf + c));
-          dot = fmaf(x.x, y.x, dot);
-          dot = fmaf(x.y, y.y, dot);
-          dot = fmaf(x.z, y.z, dot);
-          dot = fmaf(x.w, y.w, dot);
+  const bool vec = (k & 3) == 0 && k <= 128;
+  if (vec) {
+    // the user's row stays in registers: lane gl of every group owns the float4 chunks gl, gl+8, gl+16, gl+24
+    float4 uc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 4 * (gl + 8 * j);
+      uc[j] = c < k ? __ldg(reinterpret_cast<const float4*>(uf + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int j0 = 0; j0 < n; j0 += 4) {     // uniform trip count for the whole warp
+      const int j = j0 + grp;
+      const bool ok = j < n;
+      float dot = 0.f;
+      if (ok) {
+        const int it = __ldg(a.rows.indx + beg + j);
+        const float* vf = a.V + (size_t)it * k;
+        float4 y[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = 4 * (gl + 8 * q);
+          y[q] = c < k ? __ldg(reinterpret_cast<const float4*>(vf + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      } else {
-        for (int c = gl; c < k; c += 8) dot = fmaf(__ldg(uf + c), __ldg(vf + c), dot);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          dot = fmaf(uc[q].x, y[q].x, dot);
+          dot = fmaf(uc[q].y, y[q].y, dot);
+          dot = fmaf(uc[q].z, y[q].z, dot);
+          dot = fmaf(uc[q].w, y[q].w, dot);
+        }
+      }
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      if (ok && gl == 0) {
+        const double pred = (double)dot + a.shift;
+        const double diff = (double)__ldg(a.rows.vals + beg + j) - pred;
+        sd2 += diff * diff;
+        sp += pred;
       }
     }
-    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-    if (ok && gl == 0) {
-      const double pred = (double)dot + a.shift;
-      const double diff = (double)__ldg(a.rows.vals + beg + j) - pred;
-      sd2 += diff * diff;
-      sp += pred;
+  } else {
+    for (int j0 = 0; j0 < n; j0 += 4) {
+      const int j = j0 + grp;
+      const bool ok = j < n;
+      float dot = 0.f;
+      if (ok) {
+        const int it = __ldg(a.rows.indx + beg + j);
+        const float* vf = a.V + (size_t)it * k;
+        for (int c = gl; c < k; c += 8) dot = fmaf(__ldg(uf + c), __ldg(vf + c), dot);
+      }
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      if (ok && gl == 0) {
+        const double pred = (double)dot + a.shift;
+        const double diff = (double)__ldg(a.rows.vals + beg + j) - pred;
+        sd2 += diff * diff;
+        sp += pred;
+      }
     }
   }
   sd2 = warp_sum(sd2);
