@@ -30,18 +30,19 @@ enum { MODE_FUSED = 0, MODE_PARTIAL = 1, MODE_REDUCE = 2 };
 
 constexpr int kStageRows = 32;  // ratings staged per smem tile in the primal kernels
 
-// linear tile index -> (I, L); t >= ntri addresses the right-hand-side tile row I = mt
-__device__ __forceinline__ void tile_coords(int t, int mt, int ntri, int& I, int& L) {
-  if (t < ntri) {
-    int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-    while (i * (i + 1) / 2 > t) --i;
-    while ((i + 1) * (i + 2) / 2 <= t) ++i;
-    I = i;
-    L = t - i * (i + 1) / 2;
-  } else {
-    I = mt;
-    L = t - ntri;
+// linear tile index -> (I, L).  Column-major enumeration of the bordered lower triangle: column L
+// holds the tiles (L,L), (L+1,L), ..., (mt-1,L) and the right-hand-side tile (mt,L), i.e. mt-L+1
+// consecutive indices.  A warp therefore owns (parts of) one or two tile columns: in step J of the
+// factorisation the warps whose columns are <= J have nothing left to do and skip the phase as a
+// whole, and the active warps are fully populated (the row-major order left every warp ~1/3 full).
+__device__ __forceinline__ void tile_coords(int t, int mt, int /*ntri*/, int& I, int& L) {
+  int l = 0, rem = t;
+  while (rem >= mt - l + 1) {
+    rem -= mt - l + 1;
+    ++l;
   }
+  L = l;
+  I = l + rem;
 }
 
 __device__ __forceinline__ float rsqrt_fast(float x) {

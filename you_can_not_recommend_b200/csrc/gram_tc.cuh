@@ -364,6 +364,13 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
   } else {
     // ============================ epilogue ============================
     const int m = tid;  // TMEM lane == row of X; warp w may only touch lanes 32w .. 32w+31
+    constexpr int EPI_TPT = (NTILES + kTcEpiThreads - 1) / kTcEpiThreads;
+    int eI[EPI_TPT], eL[EPI_TPT];   // this thread's output tiles, the same for every item
+#pragma unroll
+    for (int j = 0; j < EPI_TPT; ++j) {
+      eI[j] = eL[j] = 0;
+      if (tid + j * kTcEpiThreads < NTILES) tile_coords(tid + j * kTcEpiThreads, KT, NTRI, eI[j], eL[j]);
+    }
     uint32_t itc = 0;
     for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
       const uint32_t buf = itc & 1u, aph = (itc >> 1) & 1u;
@@ -396,9 +403,11 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
       mbar_arrive(acce0 + 8 * buf);
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
       float* out = a.partial + (size_t)it * NTILES * 16;
-      for (int t = tid; t < NTILES; t += kTcEpiThreads) {
-        int I, L;
-        tile_coords(t, KT, NTRI, I, L);
+#pragma unroll
+      for (int j = 0; j < EPI_TPT; ++j) {
+        const int t = tid + j * kTcEpiThreads;
+        if (t >= NTILES) break;
+        const int I = eI[j], L = eL[j];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4 o;

@@ -66,12 +66,14 @@ struct DevBuf {
 
 // ---- row classification -------------------------------------------------------------
 constexpr int kDualBins = 6;  // MT_MAX = 4, 8, 12, 16, 20, 24  (n <= 16 .. 96)
+constexpr int kMaxChunks = 8;
+constexpr int kMinItemsPerChunk = 4 * 148;   // a persistent Gram launch needs a few items per SM
 
 struct WorkPlan {
   // host-side lists (indices into the row list)
   std::vector<int32_t> dual[kDualBins];
   std::vector<int32_t> fused;
-  std::vector<int32_t> multi, multi_first_item, multi_n_items;
+  std::vector<int32_t> multi, multi_first_item, multi_n_items, multi_len;
   std::vector<int32_t> item_row, item_off;
   int64_t ratings_dual[kDualBins] = {0};
   int64_t ratings_fused = 0, ratings_multi = 0;
@@ -98,6 +100,7 @@ void classify(const int32_t* row_len, int n_rows, int dual_max, int split_cols, 
         ++cnt;
       }
       w.multi_n_items.push_back(cnt);
+      w.multi_len.push_back(n);
       w.ratings_multi += n;
     }
   }
@@ -116,6 +119,12 @@ struct DevPlan {
   int64_t ratings_dual[kDualBins] = {0};
   int64_t ratings_fused = 0, ratings_multi = 0;
   size_t words = 0;
+  // split rows in up to kMaxChunks groups of equal ratings: the Gram of group c+1 overlaps the
+  // reduce+solve of group c on a second stream
+  int n_chunks = 1;
+  int chunk_row[kMaxChunks + 1] = {0};
+  int chunk_item[kMaxChunks + 1] = {0};
+  int64_t chunk_ratings[kMaxChunks] = {0};
 };
 
 size_t plan_words(const WorkPlan& w) {
@@ -125,7 +134,7 @@ size_t plan_words(const WorkPlan& w) {
   return n;
 }
 
-void pack_plan(const WorkPlan& w, int32_t* host, DevPlan& p) {
+void pack_plan(const WorkPlan& w, int32_t* host, DevPlan& p, int max_chunks) {
   size_t o = 0;
   auto put = [&](const std::vector<int32_t>& v, size_t& off) {
     off = o;
@@ -149,6 +158,30 @@ void pack_plan(const WorkPlan& w, int32_t* host, DevPlan& p) {
   p.ratings_fused = w.ratings_fused;
   p.ratings_multi = w.ratings_multi;
   p.words = o;
+  // chunk cuts at equal cumulative ratings
+  const int nm = (int)w.multi.size();
+  int chunks = (int)std::min<int64_t>(std::min(kMaxChunks, max_chunks), (int64_t)w.item_row.size() / kMinItemsPerChunk);
+  if (chunks < 2) chunks = 1;
+  p.n_chunks = chunks;
+  p.chunk_row[0] = 0;
+  p.chunk_item[0] = 0;
+  int64_t acc = 0, done = 0;
+  int c = 1;
+  for (int m = 0; m < nm && c < chunks; ++m) {
+    acc += w.multi_len[m];
+    if (acc >= w.ratings_multi * c / chunks) {
+      p.chunk_row[c] = m + 1;
+      p.chunk_item[c] = w.multi_first_item[m] + w.multi_n_items[m];
+      p.chunk_ratings[c - 1] = acc - done;
+      done = acc;
+      ++c;
+    }
+  }
+  for (; c <= chunks; ++c) {   // last cut (and any cut the loop did not reach)
+    p.chunk_row[c] = nm;
+    p.chunk_item[c] = (int)w.item_row.size();
+    if (c - 1 < kMaxChunks) { p.chunk_ratings[c - 1] = w.ratings_multi - done; done = w.ratings_multi; }
+  }
 }
 
 struct RowSet {
@@ -193,6 +226,9 @@ struct ycnr_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D of portion inputs, overlaps the previous portion's kernels
   cudaEvent_t copied = nullptr;
+  cudaStream_t aux_stream = nullptr;    // reduce+solve of split rows, overlapping the next Gram chunk
+  cudaEvent_t chunk_ev[kMaxChunks + 2] = {nullptr};
+  bool aux_pending = false;
   std::vector<std::pair<const char*, size_t>> pinned;  // ycnr_host_register regions
   float* d_fac[2] = {nullptr, nullptr};
   float* h_fac[2] = {nullptr, nullptr};
@@ -234,8 +270,10 @@ DstList make_dst(ycnr_ctx* c, int which) {
 struct ProfScope {
   ycnr_ctx* c;
   int cls;
+  cudaStream_t st;
   cudaEvent_t a = nullptr, b = nullptr;
-  ProfScope(ycnr_ctx* ctx, int cls_, int64_t rows, int64_t ratings) : c(ctx), cls(cls_) {
+  ProfScope(ycnr_ctx* ctx, int cls_, int64_t rows, int64_t ratings, cudaStream_t stream = nullptr)
+      : c(ctx), cls(cls_), st(stream ? stream : ctx->stream) {
     c->prof.launches[cls]++;
     c->prof.rows[cls] += rows;
     c->prof.ratings[cls] += ratings;
@@ -249,18 +287,18 @@ struct ProfScope {
     };
     a = get();
     b = get();
-    cudaEventRecord(a, c->stream);
+    cudaEventRecord(a, st);
   }
   ~ProfScope() {
     if (!a) return;
-    cudaEventRecord(b, c->stream);
+    cudaEventRecord(b, st);
     c->prof_open.push_back({cls, a, b});
   }
 };
 
 // ---- kernel dispatch -----------------------------------------------------------------
 template <int KT>
-int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int n_items, int64_t ratings) {
+int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int item_from, int n_items, int64_t ratings) {
   using namespace ycnr;
   if constexpr (4 * KT + 4 > 128) {
     return fail("tcgen05 Gram path supports factorsCount <= 124");
@@ -269,11 +307,12 @@ int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int n_items, int64_t
     t.rows = pa.rows;
     t.fixed = pa.fixed;
     t.k = pa.k;
-    t.item_row = pa.item_row;
-    t.item_off = pa.item_off;
+    constexpr int NTILES = KT * (KT + 1) / 2 + KT;
+    t.item_row = pa.item_row + item_from;
+    t.item_off = pa.item_off + item_from;
     t.n_items = n_items;
     t.split_cols = pa.split_cols;
-    t.partial = pa.partial;
+    t.partial = pa.partial + (size_t)item_from * NTILES * 16;
     t.variant = (uint32_t)c->opts.tc_variant;
     const size_t smem = gram_tc_smem_bytes<KT>();
     static bool configured = false;
@@ -305,16 +344,35 @@ int launch_primal_kt(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p
     a.item_row = plan_base + p.off_item_row;
     a.item_off = plan_base + p.off_item_off;
     a.partial = (float*)c->partial.p;
-    if (c->use_tc) {
-      OK((launch_gram_tc<KT>(c, a, p.n_items, p.ratings_multi)));
-    } else {
-      ProfScope ps(c, YCNR_K_GRAM_PARTIAL, p.n_items, p.ratings_multi);
-      als_primal_kernel<KT, NT, 1, MODE_PARTIAL><<<p.n_items, NT, 0, c->stream>>>(a);
-    }
     a.work = plan_base + p.off_multi;
     a.row_first_item = plan_base + p.off_multi_first;
     a.row_n_items = plan_base + p.off_multi_n;
-    {
+    if (c->use_tc && p.n_chunks > 1) {
+      // Gram of chunk i+1 (tensor pipe / shared memory) overlaps reduce+solve of chunk i (FFMA, barrier
+      // latency) on the aux stream; both kernels fit on an SM together.  The caller joins the aux stream.
+      for (int ch = 0; ch < p.n_chunks; ++ch) {
+        const int i0 = p.chunk_item[ch], i1 = p.chunk_item[ch + 1];
+        const int m0 = p.chunk_row[ch], m1 = p.chunk_row[ch + 1];
+        if (i1 > i0) OK((launch_gram_tc<KT>(c, a, i0, i1 - i0, p.chunk_ratings[ch])));
+        CU(cudaEventRecord(c->chunk_ev[ch], c->stream));
+        CU(cudaStreamWaitEvent(c->aux_stream, c->chunk_ev[ch], 0));
+        if (m1 > m0) {
+          PrimalArgs r = a;
+          r.work = a.work + m0;
+          r.row_first_item = a.row_first_item + m0;
+          r.row_n_items = a.row_n_items + m0;
+          ProfScope ps(c, YCNR_K_REDUCE_SOLVE, m1 - m0, 0, c->aux_stream);
+          als_primal_kernel<KT, NT, 1, MODE_REDUCE><<<m1 - m0, NT, 0, c->aux_stream>>>(r);
+        }
+      }
+      c->aux_pending = true;
+    } else {
+      if (c->use_tc) {
+        OK((launch_gram_tc<KT>(c, a, 0, p.n_items, p.ratings_multi)));
+      } else {
+        ProfScope ps(c, YCNR_K_GRAM_PARTIAL, p.n_items, p.ratings_multi);
+        als_primal_kernel<KT, NT, 1, MODE_PARTIAL><<<p.n_items, NT, 0, c->stream>>>(a);
+      }
       ProfScope ps(c, YCNR_K_REDUCE_SOLVE, p.n_multi, 0);
       als_primal_kernel<KT, NT, 1, MODE_REDUCE><<<p.n_multi, NT, 0, c->stream>>>(a);
     }
@@ -370,12 +428,6 @@ int run_als(ycnr_ctx* c, int step_type, const RowsView& view, const DevPlan& p, 
   d.pitch = dual_pitch(c->k);
   d.lambda = lambda;
   d.dst = make_dst(c, solved);
-  OK((launch_dual_bin<4, 32>(c, d, p.n_dual[0], p.ratings_dual[0], plan_base + p.off_dual[0])));
-  OK((launch_dual_bin<8, 64>(c, d, p.n_dual[1], p.ratings_dual[1], plan_base + p.off_dual[1])));
-  OK((launch_dual_bin<12, 96>(c, d, p.n_dual[2], p.ratings_dual[2], plan_base + p.off_dual[2])));
-  OK((launch_dual_bin<16, 160>(c, d, p.n_dual[3], p.ratings_dual[3], plan_base + p.off_dual[3])));
-  OK((launch_dual_bin<20, 256>(c, d, p.n_dual[4], p.ratings_dual[4], plan_base + p.off_dual[4])));
-  OK((launch_dual_bin<24, 352>(c, d, p.n_dual[5], p.ratings_dual[5], plan_base + p.off_dual[5])));
   ycnr::PrimalArgs a{};
   a.rows = view;
   a.fixed = c->d_fac[fixed];
@@ -383,7 +435,21 @@ int run_als(ycnr_ctx* c, int step_type, const RowsView& view, const DevPlan& p, 
   a.lambda = lambda;
   a.dst = d.dst;
   a.split_cols = c->split_cols;
+  // long rows first: their reduce+solve chunks run on the aux stream under the dual kernels too
+  CU(cudaEventRecord(c->chunk_ev[kMaxChunks], c->stream));
+  CU(cudaStreamWaitEvent(c->aux_stream, c->chunk_ev[kMaxChunks], 0));   // aux starts after everything queued so far
   OK(launch_primal(c, a, p, plan_base));
+  OK((launch_dual_bin<4, 32>(c, d, p.n_dual[0], p.ratings_dual[0], plan_base + p.off_dual[0])));
+  OK((launch_dual_bin<8, 64>(c, d, p.n_dual[1], p.ratings_dual[1], plan_base + p.off_dual[1])));
+  OK((launch_dual_bin<12, 96>(c, d, p.n_dual[2], p.ratings_dual[2], plan_base + p.off_dual[2])));
+  OK((launch_dual_bin<16, 160>(c, d, p.n_dual[3], p.ratings_dual[3], plan_base + p.off_dual[3])));
+  OK((launch_dual_bin<20, 256>(c, d, p.n_dual[4], p.ratings_dual[4], plan_base + p.off_dual[4])));
+  OK((launch_dual_bin<24, 352>(c, d, p.n_dual[5], p.ratings_dual[5], plan_base + p.off_dual[5])));
+  if (c->aux_pending) {
+    CU(cudaEventRecord(c->chunk_ev[kMaxChunks + 1], c->aux_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[kMaxChunks + 1], 0));
+    c->aux_pending = false;
+  }
   c->device_current[solved] = true;
   return 0;
 }
@@ -500,7 +566,7 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
   }
   int32_t pf[2] = {0, R};
   memcpy(h + o_pf, pf, 8);
-  if (with_plan) pack_plan(w, (int32_t*)(h + o_plan), s.plan);
+  if (with_plan) pack_plan(w, (int32_t*)(h + o_plan), s.plan, c->opts.solve_chunks);
   char* d = (char*)sl.dev.p;
   // (the f64 scratch section is not meaningful on the host side, but it sits inside the range)
   if (direct) {
@@ -602,6 +668,8 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->copied, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+  for (auto& e : c->chunk_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (int w = 0; w < 2; ++w) CU(cudaMalloc(&c->d_fac[w], (size_t)c->fac_rows[w] * c->k * sizeof(float)));
   *out = c;
   return 0;
@@ -612,6 +680,7 @@ int ycnr_destroy(ycnr_ctx* c) {
   cudaSetDevice(c->opts.device);
   cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->stream);
+  if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
   collect_profile(c);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (int w = 0; w < 2; ++w) {
@@ -628,6 +697,8 @@ int ycnr_destroy(ycnr_ctx* c) {
   c->gather_tmp.release();
   for (auto& r : c->pinned) cudaHostUnregister((void*)r.first);
   if (c->copied) cudaEventDestroy(c->copied);
+  for (auto e : c->chunk_ev) if (e) cudaEventDestroy(e);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -917,7 +988,7 @@ int ycnr_rowset_create(ycnr_ctx* c, int32_t step_type, int32_t n_rows, const int
     WorkPlan w;
     classify(row_len, n_rows, c->dual_max, c->split_cols, c->fused_max, w);
     packed.resize(plan_words(w) + 1);
-    pack_plan(w, packed.data(), rs.dplan);
+    pack_plan(w, packed.data(), rs.dplan, c->opts.solve_chunks);
     OK(rs.plan.ensure(packed.size() * 4));
     CU(cudaMemcpyAsync(rs.plan.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, c->stream));
   } else {

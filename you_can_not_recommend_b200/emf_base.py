@@ -37,7 +37,7 @@ def default_options():
         "shared": {"userFactorsShmKey": -1, "itemFactorsShmKey": -1, "portionBufferShmKeys": {}},
         # --- additions of the B200 path (not in the reference) ---
         "gpu": {"device": 0, "gramPath": "auto", "dualMaxCols": -1, "splitCols": 0, "profile": False,
-                "bulk": False, "cachePortions": False, "tcMinCols": 0},
+                "bulk": False, "cachePortions": False, "tcMinCols": 0, "solveChunks": 0},
         "seed": front_end.DEFAULT_SEED,
     }
 
@@ -114,7 +114,8 @@ class EmfBase:
         self.ctx = native.Context(
             self.factorsCount, self.totalUsersCount, self.totalItemsCount,
             o["als"]["userFactReg"], o["als"]["itemFactReg"], False, False, dev,
-            _GRAM[g["gramPath"]], g["dualMaxCols"], g["splitCols"], g["profile"], g.get("tcMinCols", 0))
+            _GRAM[g["gramPath"]], g["dualMaxCols"], g["splitCols"], g["profile"], g.get("tcMinCols", 0),
+            solve_chunks=g.get("solveChunks", 0))
         self.ctx.attach_factors(self.userFactors, self.itemFactors)
         return self.ctx
 

@@ -35,7 +35,7 @@ class Options(C.Structure):
         ("use_double_precision", C.c_int32), ("lowmem", C.c_int32), ("device", C.c_int32),
         ("gram_path", C.c_int32), ("dual_max_cols", C.c_int32), ("split_cols", C.c_int32),
         ("profile", C.c_int32), ("tc_min_cols", C.c_int32), ("tc_variant", C.c_int32),
-        ("reserved", C.c_int32 * 2),
+        ("solve_chunks", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -94,13 +94,13 @@ class Context:
 
     def __init__(self, factors_count, total_users, total_items, user_fact_reg=0.05, item_fact_reg=0.05,
                  use_double_precision=False, lowmem=False, device=0, gram_path=GRAM_AUTO, dual_max_cols=-1,
-                 split_cols=0, profile=False, tc_min_cols=0, tc_variant=0):
+                 split_cols=0, profile=False, tc_min_cols=0, tc_variant=0, solve_chunks=0):
         o = Options()
         o.factors_count, o.total_users, o.total_items = factors_count, total_users, total_items
         o.user_fact_reg, o.item_fact_reg = user_fact_reg, item_fact_reg
         o.use_double_precision, o.lowmem, o.device = int(use_double_precision), int(lowmem), device
         o.gram_path, o.dual_max_cols, o.split_cols, o.profile = gram_path, dual_max_cols, split_cols, int(profile)
-        o.tc_min_cols, o.tc_variant = tc_min_cols, tc_variant
+        o.tc_min_cols, o.tc_variant, o.solve_chunks = tc_min_cols, tc_variant, solve_chunks
         self._h = C.c_void_p()
         self.k, self.total_users, self.total_items = factors_count, total_users, total_items
         self._keep = []
