@@ -194,11 +194,31 @@ def run_reference(args):
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_line(line)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Libraries print to fd 1 (NCCL's version banner, for one): route fd 1 to stderr for the whole run
+    and keep the real stdout for the single JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
     args = parse_args()
+    protect_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -228,8 +248,7 @@ def main():
     m = EmfMaster(table, opts, rank=rank, world=world)
     m.prepareToTrain()
     if world > 1 and args.fused_peers:
-        for which in (native.USER_FACTORS, native.ITEM_FACTORS):
-            ydist.connect_peers(m.ctx, which, rank, world)
+        m.connectPeers()
     stream = torch.cuda.ExternalStream(m.ctx.stream_ptr(), device=torch.device("cuda", local))
     for _ in range(args.warmup):
         m.trainIter()
@@ -310,6 +329,7 @@ def main():
         torch.cuda.synchronize()
         barrier()
         m2.h2d_bytes = m2.d2h_bytes = 0
+        m2.phase_ms = {}
         n_e2e = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         for _ in range(n_e2e):
@@ -328,6 +348,7 @@ def main():
             h2d, d2h = float(bb[0]), float(bb[1])
         e2e = {"value": table.nnz / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "ratings_in_portion": args.e2e_portion,
+               "phase_ms": {k_: v_ / n_e2e for k_, v_ in m2.phase_ms.items()},
                "api": "EmfWorker calcTrainAlsPortion/calcRmsePortion messages -> ycnr_als_portion/ycnr_rmse_portion",
                "inputs": "converted portions cached in page-locked host memory (usePortionsCache); H2D of every portion and D2H of the solved rows inside the timed region"}
         m2.endTrain()
@@ -352,7 +373,7 @@ def main():
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches,
             "clocks": clocks, "rmse": last,
         }
-        print(json.dumps(line))
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -104,8 +104,21 @@ void classify(const int32_t* row_len, int n_rows, int dual_max, int split_cols, 
       w.ratings_multi += n;
     }
   }
+  // longest rows first inside every launch (ties: list order).  Dual rows have at most 16 distinct
+  // lengths per bin: a stable counting sort, O(rows) — this runs per portion on the e2e path.
   auto by_len_desc = [&](int32_t a, int32_t b) { return row_len[a] != row_len[b] ? row_len[a] > row_len[b] : a < b; };
-  for (auto& d : w.dual) std::sort(d.begin(), d.end(), by_len_desc);
+  std::vector<int32_t> tmp;
+  for (int b = 0; b < kDualBins; ++b) {
+    auto& d = w.dual[b];
+    if (d.size() < 2) continue;
+    const int hi = 16 * (b + 1);          // lengths of this bin: hi-15 .. hi
+    size_t cnt[17] = {0};
+    for (int32_t r : d) cnt[hi - row_len[r] + 1]++;
+    for (int i = 1; i <= 16; ++i) cnt[i] += cnt[i - 1];
+    tmp.resize(d.size());
+    for (int32_t r : d) tmp[cnt[hi - row_len[r]]++] = r;
+    d.swap(tmp);
+  }
   std::sort(w.fused.begin(), w.fused.end(), by_len_desc);
 }
 
@@ -204,6 +217,7 @@ struct Slot {  // staging for the per-portion path
   size_t host_cap = 0;
   DevBuf dev;
   cudaEvent_t done = nullptr;
+  cudaEvent_t solved = nullptr;   // kernels of the portion finished: its rows may be copied back
   bool pending = false;
 };
 constexpr int kSlots = 4;
@@ -226,6 +240,8 @@ struct ycnr_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D of portion inputs, overlaps the previous portion's kernels
   cudaEvent_t copied = nullptr;
+  cudaStream_t d2h_stream = nullptr;    // solved rows -> host factor segment, overlaps the next portion
+  bool d2h_pending = false;
   cudaStream_t aux_stream = nullptr;    // reduce+solve of split rows, overlapping the next Gram chunk
   cudaEvent_t chunk_ev[kMaxChunks + 2] = {nullptr};
   bool aux_pending = false;
@@ -540,6 +556,7 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
     sl.pending = false;
   }
   if (!sl.done) CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  if (!sl.solved) CU(cudaEventCreateWithFlags(&sl.solved, cudaEventDisableTiming));
   // ratings that already sit in page-locked caller memory are DMA'd from there
   auto is_pinned = [&](const void* p, size_t bytes) {
     const char* q = (const char*)p;
@@ -582,8 +599,10 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
   }
   CU(cudaEventRecord(c->copied, c->copy_stream));
   CU(cudaStreamWaitEvent(c->stream, c->copied, 0));
-  // blocking with respect to the caller's buffers: they may be refilled once we return
-  if (direct) CU(cudaEventSynchronize(c->copied));
+  // Unregistered caller buffers were copied into the slot above and may be refilled once we return.
+  // Regions registered with ycnr_host_register are a portion CACHE (usePortionsCache): they are DMA'd
+  // asynchronously and must stay unmodified until the step ends (ycnr_end_train_step / the return of
+  // ycnr_rmse_portion) — no host wait here, so the copy engine stays busy while the host plans ahead.
   s.view.row_start = (const int64_t*)(d + o_start);
   s.view.row_ids = (const int32_t*)(d + o_ids);
   s.view.row_len = (const int32_t*)(d + o_len);
@@ -669,6 +688,7 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->copied, cudaEventDisableTiming));
   CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
   for (auto& e : c->chunk_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (int w = 0; w < 2; ++w) CU(cudaMalloc(&c->d_fac[w], (size_t)c->fac_rows[w] * c->k * sizeof(float)));
   *out = c;
@@ -681,6 +701,7 @@ int ycnr_destroy(ycnr_ctx* c) {
   cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->stream);
   if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
+  if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
   collect_profile(c);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (int w = 0; w < 2; ++w) {
@@ -692,6 +713,7 @@ int ycnr_destroy(ycnr_ctx* c) {
     if (s.host) cudaFreeHost(s.host);
     s.dev.release();
     if (s.done) cudaEventDestroy(s.done);
+    if (s.solved) cudaEventDestroy(s.solved);
   }
   c->partial.release();
   c->gather_tmp.release();
@@ -699,6 +721,7 @@ int ycnr_destroy(ycnr_ctx* c) {
   if (c->copied) cudaEventDestroy(c->copied);
   for (auto e : c->chunk_ev) if (e) cudaEventDestroy(e);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -817,7 +840,20 @@ int ycnr_als_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, cons
   OK(stage_portion(c, rows, indx, vals, true, s));
   if (s.n_rows > 0) {
     OK(run_als(c, c->step_type, s.view, s.plan, s.plan_base));
-    c->solved_ranges.emplace_back(s.first_row, s.last_row);
+    const int solved = c->step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
+    if (c->h_fac[solved] && c->h_registered[solved]) {
+      // the portion's row-id range goes back to the host segment on its own stream as soon as its kernels
+      // are done, under the next portion's kernels (portions cover disjoint ascending id ranges)
+      CU(cudaEventRecord(s.slot->solved, c->stream));
+      CU(cudaStreamWaitEvent(c->d2h_stream, s.slot->solved, 0));
+      const size_t off = (size_t)s.first_row * c->k;
+      CU(cudaMemcpyAsync(c->h_fac[solved] + off, c->d_fac[solved] + off,
+                         (size_t)(s.last_row - s.first_row + 1) * c->k * sizeof(float), cudaMemcpyDeviceToHost,
+                         c->d2h_stream));
+      c->d2h_pending = true;
+    } else {
+      c->solved_ranges.emplace_back(s.first_row, s.last_row);   // pageable segment: one merged copy at the end
+    }
   }
   OK(finish_slot(c, s.slot));
   if (info) {
@@ -851,6 +887,10 @@ int ycnr_end_train_step(ycnr_ctx* c) {
     }
   }
   CU(cudaStreamSynchronize(c->stream));
+  if (c->d2h_pending) {
+    CU(cudaStreamSynchronize(c->d2h_stream));
+    c->d2h_pending = false;
+  }
   c->solved_ranges.clear();
   c->step_type = -1;
   return 0;

@@ -64,10 +64,23 @@ def all_ranges(my_range, world, group=None):
     return out
 
 
+_grouped_ok = True
+
+
 def broadcast_ranges(mat, ranges, group=None):
     """mat: 2-D torch tensor replica (rows x k) on every rank; rank r owns rows ranges[r].
-    All-gather with unequal counts = one broadcast per non-empty range, issued together."""
+    All-gather with unequal counts, in place: the output list is views of the replica itself (NCCL runs
+    it as one group of broadcasts); ranks with an empty range fall back to one broadcast per range."""
     import torch.distributed as dist
+    rank = dist.get_rank(group)
+    global _grouped_ok
+    if _grouped_ok and all(b > a for a, b in ranges) and dist.get_backend(group) == "nccl":
+        views = [mat[a:b] for a, b in ranges]
+        try:
+            dist.all_gather(views, views[rank], group=group)
+            return
+        except (RuntimeError, ValueError, TypeError):   # argument check of an older torch: nothing was enqueued
+            _grouped_ok = False
     works = []
     for r, (a, b) in enumerate(ranges):
         if b > a:
@@ -115,20 +128,31 @@ def connect_peers(ctx, which, rank, world, group=None):
     return ptrs
 
 
+def barrier(group=None):
+    import torch.distributed as dist
+    dist.barrier(group=group)
+
+
 def reduce_rmse(sums, last, group=None):
     """Combine (rSumDiff2, rCnt, rSum) over ranks in rank order; `last` = partials of the globally
-    last portion = the highest rank that had any portion."""
+    last portion = the highest rank that had any portion ('rmseSaveCalcs', EmfMaster.js:726-736,770-783).
+    One all-gather of six doubles per rank (device tensors under NCCL, CPU tensors under gloo)."""
+    import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    out = [None] * world
-    dist.all_gather_object(out, (tuple(float(x) for x in sums),
-                                 None if last is None else {"rSum": float(last["rSum"]), "rCnt": float(last["rCnt"])}),
-                           group=group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.tensor([float(sums[0]), float(sums[1]), float(sums[2]),
+                         0.0 if last is None else float(last["rSum"]),
+                         0.0 if last is None else float(last["rCnt"]),
+                         0.0 if last is None else 1.0], dtype=torch.float64, device=dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    rows = torch.stack(parts).cpu().tolist()
     tot = [0.0, 0.0, 0.0]
     glast = None
-    for s, l in out:
+    for r in rows:                      # rank order: deterministic sums
         for i in range(3):
-            tot[i] += s[i]
-        if l is not None:
-            glast = l
+            tot[i] += r[i]
+        if r[5] != 0.0:
+            glast = {"rSum": r[3], "rCnt": r[4]}
     return tuple(tot), glast

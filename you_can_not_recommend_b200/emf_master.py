@@ -17,6 +17,7 @@ contiguous nnz-balanced slices per rank and the solved slices are exchanged afte
 half-step (dist.py), replacing 'alsSaveCalcedFactors' (EmfMaster.js:711-723).
 """
 import math
+import time
 
 import numpy as np
 
@@ -51,6 +52,9 @@ class EmfMaster(EmfBase):
         self._lastRmseMsg = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.fusedPeers = False
+        self._ranges = {}
+        self.phase_ms = {}
 
     # ---- prepare ---------------------------------------------------------------------------
     def splitDataForTrain(self):
@@ -233,9 +237,22 @@ class EmfMaster(EmfBase):
         if self.world > 1:
             self._refresh_replicas(stepType)
 
+    def connectPeers(self):
+        """Fused all-gather ('alsSaveCalcedFactors' without a separate exchange step): the solve kernels
+        store every solved row into all replicas over NVLink; a half-step then ends with one barrier."""
+        for which in (native.USER_FACTORS, native.ITEM_FACTORS):
+            ydist.connect_peers(self.ctx, which, self.rank, self.world, self.group)
+        self.fusedPeers = True
+
     def _refresh_replicas(self, stepType):
         which = native.USER_FACTORS if stepType == "byUser" else native.ITEM_FACTORS
-        ranges = ydist.all_ranges(self._solved_range(stepType), self.world, self.group)
+        if self.fusedPeers and self.options["gpu"]["bulk"]:
+            self.ctx.synchronize()          # my peer stores are complete ...
+            ydist.barrier(self.group)       # ... and so are everybody else's into my replica
+            return
+        if stepType not in self._ranges:    # static per step: the portion plan does not change between iterations
+            self._ranges[stepType] = ydist.all_ranges(self._solved_range(stepType), self.world, self.group)
+        ranges = self._ranges[stepType]
         ydist.refresh_replicas(self.ctx, which, self.factorsCount, ranges, self.rank, self.group,
                                host=None if self.options["gpu"]["bulk"] else
                                (self.userFactors if which == 0 else self.itemFactors))
@@ -302,13 +319,24 @@ class EmfMaster(EmfBase):
         return self.rmse
 
     # ---- train loop ------------------------------------------------------------------------------
+    def _timed(self, name, fn, *args):
+        """Per-portion mode only (every phase ends host-synchronous there): wall time per phase, the
+        analogue of the reference's per-step console timings (EmfLord.js:1075-1077)."""
+        if self.options["gpu"]["bulk"]:
+            return fn(*args)
+        t0 = time.perf_counter()
+        out = fn(*args)
+        self.phase_ms[name] = self.phase_ms.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return out
+
     def trainIter(self):
         """One pass of the loop body of EmfLord.train (EmfLord.js:892-902)."""
-        self.alsTrainIter()
+        self._timed("byUser", self.alsTrainStep, "byUser")
+        self._timed("byItem", self.alsTrainStep, "byItem")
         out = {
-            "rmseValidate": self.calcRmse("rmseValidate", False),
-            "rmseTest": self.calcRmse("rmseTest", False),
-            "rmseTestShift": self.calcRmse("rmseTest", True),
+            "rmseValidate": self._timed("rmseValidate", self.calcRmse, "rmseValidate", False),
+            "rmseTest": self._timed("rmseTest", self.calcRmse, "rmseTest", False),
+            "rmseTestShift": self._timed("rmseTestShift", self.calcRmse, "rmseTest", True),
             "globalAvgShift": self.globalAvgShift,
         }
         self.history.append(out)
