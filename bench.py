@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mal", choices=["mal", "netflix", "ml-1m", "ml-100k"])
     ap.add_argument("--factors", type=int, default=0)
-    ap.add_argument("--e2e-portion", type=int, default=2_000_000, help="ratingsInPortionForAls of the e2e leg")
+    ap.add_argument("--e2e-portion", type=int, default=8_000_000, help="ratingsInPortionForAls of the e2e leg")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -201,6 +201,7 @@ __device__ __forceinline__ void tile_cholesky_solve(float (&acc)[TPT][4][4], con
 struct PrimalArgs {
   RowsView rows;
   const float* __restrict__ fixed;  // F, row-major, k columns
+  size_t fixed_bytes;               // size of F (decides whether the Gram loaders prefetch into L2)
   int k;
   double lambda;
   DstList dst;                      // S replicas
@@ -391,6 +392,17 @@ struct DualArgs {
   const int32_t* __restrict__ work;
 };
 
+constexpr int kDualMaxSplit = 8;   // largest K-split of the Gram sweep (k = 100: 25 chunks of 4 columns)
+
+// tiles of the bordered lower triangle of an mt x mt tile system (Gram tiles + rhs tile row)
+__host__ __device__ constexpr int dual_ntl(int mt) { return mt * (mt + 1) / 2 + mt; }
+// floats of K-split scratch a CTA of NT threads needs for systems of exactly mt tile rows
+__host__ __device__ constexpr int dual_red_floats(int mt, int nt) {
+  int g = nt / dual_ntl(mt);
+  if (g > kDualMaxSplit) g = kDualMaxSplit;
+  return g > 1 ? (g - 1) * dual_ntl(mt) * 16 : 0;
+}
+
 template <int MT_MAX, int NT>
 __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
   constexpr int NMAX = 4 * MT_MAX;
@@ -401,6 +413,7 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
   float* minv = panel + (MT_MAX + 1) * 16;     // MT_MAX x 16
   float* ysm = minv + MT_MAX * 16;             // NMAX
   float* vs = ysm + NMAX;                      // NMAX
+  float* red = vs + NMAX;                      // K-split partial tiles: [G-1][4][ntl] float4
 
   const int tid = threadIdx.x;
   const int k = a.k, pitch = a.pitch;
@@ -437,9 +450,17 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
   __syncthreads();
 
   // ---- G tiles ------------------------------------------------------------------------
+  // Thread t < ntl owns tile t for the factorisation.  The CTA has NT >= G*ntl threads: the spare ones
+  // take a share of the Gram sweep (K-split, thread g*ntl + t sums columns [c_beg, c_end) of tile t) and
+  // hand their partial tile over through shared memory; the owner adds them in group order, so the result
+  // does not depend on scheduling.
   const int ntri = mt * (mt + 1) / 2;
+  const int ntl = ntri + mt;
+  int G = NT / ntl;
+  if (G > kDualMaxSplit) G = kDualMaxSplit;
+  const int g = tid / ntl, t = tid - g * ntl;
   int tI[1], tL[1];
-  if (tid < ntri + mt) tile_coords(tid, mt, ntri, tI[0], tL[0]);
+  if (g < G) tile_coords(t, mt, ntri, tI[0], tL[0]);
   else { tI[0] = -1; tL[0] = -1; }
   float acc[1][4][4];
 #pragma unroll
@@ -447,11 +468,14 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[0][i][j] = 0.f;
 
-  if (tI[0] >= 0 && tI[0] < mt) {
+  const bool gram_tile = tI[0] >= 0 && tI[0] < mt;
+  if (gram_tile) {
     const float* ya = Y + tI[0] * pitch;
     const float* yb = Y + tL[0] * pitch;
     const int tstride = mt * pitch;
-    for (int c = 0; c < K4; c += 4) {
+    const int CHT = K4 >> 2;
+    const int c_beg = 4 * ((g * CHT) / G), c_end = 4 * (((g + 1) * CHT) / G);
+    for (int c = c_beg; c < c_end; c += 4) {
       float4 av[4], bv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -470,6 +494,30 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
           acc[0][i][j] = s;
         }
     }
+  }
+  if (G > 1) {   // uniform over the CTA
+    if (g > 0) {
+      if (gram_tile) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(red + 4 * (((g - 1) * 4 + i) * ntl + t)) =
+              make_float4(acc[0][i][0], acc[0][i][1], acc[0][i][2], acc[0][i][3]);
+      }
+      tI[0] = -1;   // helpers own no tile of the factorisation
+      tL[0] = -1;
+    }
+    __syncthreads();
+    if (g == 0 && gram_tile) {
+      for (int gg = 1; gg < G; ++gg) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(red + 4 * (((gg - 1) * 4 + i) * ntl + t));
+          acc[0][i][0] += v.x; acc[0][i][1] += v.y; acc[0][i][2] += v.z; acc[0][i][3] += v.w;
+        }
+      }
+    }
+  }
+  if (tI[0] >= 0 && tI[0] < mt) {
     if (tI[0] == tL[0]) {
       const float lam = (float)(a.lambda * (double)n);
 #pragma unroll

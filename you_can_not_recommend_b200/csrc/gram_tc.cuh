@@ -48,6 +48,7 @@ namespace ycnr {
 constexpr int kTcStageRows = 32;                              // ratings per stage (4 MMAs of K = 8)
 constexpr int kTcPanelBytes = (kTcStageRows / 8) * 1024;      // one 32-column panel of one stage
 constexpr int kTcEpiThreads = 128;
+constexpr int kTcPrefetchUses = 2;                            // L2 prefetch distance in ring cycles
 // One loader warp and one splitter warp per ring slot: a warp sees every use of "its" slot in
 // order, which is what makes waiting on an mbarrier phase PARITY sound (a warp that hopped between
 // slots could be two phases off and sail through a wait).
@@ -68,7 +69,7 @@ struct TcCfg {
   static constexpr int XS_BYTES = (NC * XP * 4 + 15) & ~15;
   static constexpr int STAGES_FIT = (kTcSmemLimit - 2048 - XS_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT < kTcMaxStages ? STAGES_FIT : kTcMaxStages;
-  static constexpr int THREADS = kTcEpiThreads + 32 + 2 * 32 * STAGES;   // epilogue | MMA | loaders | splitters
+  static constexpr int THREADS = kTcEpiThreads + 32 + 4 * 32 * STAGES;   // epilogue | MMA | 2 loaders + 2 splitters per slot
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + XS_BYTES + (3 * STAGES + 4) * 8 + 16 + 1024;
   static_assert(KP + 4 <= 128, "rhs column must fit the M = 128 accumulator");
   static_assert(NCH <= 32, "one lane per 16-byte chunk of a rating");
@@ -85,6 +86,7 @@ struct GramTcArgs {
   int n_items;
   int split_cols;
   float* __restrict__ partial;   // [items][tiles][16]
+  int prefetch;                  // 1: the fixed matrix does not fit L2, loaders prefetch far-ahead rows into it
   uint32_t variant;              // diagnostics: 16 = splitters also overwrite the H columns with explicitly masked values
 };
 
@@ -201,9 +203,9 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
     reinterpret_cast<float4*>(stage_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full0 + 8 * s, 1);
+      mbar_init(full0 + 8 * s, 2);     // two splitter warps
       mbar_init(empty0 + 8 * s, 1);
-      mbar_init(raw0 + 8 * s, 32);
+      mbar_init(raw0 + 8 * s, 64);     // every lane of the two loader warps, when its copies have landed
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf0 + 8 * b, 1);
@@ -223,7 +225,15 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 5) {
-    const bool loader = warp < 5 + STAGES;
+    // Two loader warps and two splitter warps per ring slot, each owning one half (HR ratings) of every
+    // stage of the slot.  ncu (source view, MAL byItem, one warp of each per slot): a slot's cycle was
+    // loader issue 1.8k clk -> arrival -> splitter 3k clk (LDS latency exposed) -> MMA; the epilogue and
+    // the loaders spent 97 % / 77 % of their samples waiting.  Halving the two producer legs and keeping
+    // four LDS.128 in flight in the splitter shortens the cycle; the slots stay in order per warp.
+    constexpr int HR = kTcStageRows / 2;
+    const int pw = warp - 5;
+    const bool loader = pw < 2 * STAGES;
+    const int s_own = (loader ? pw : pw - 2 * STAGES) >> 1, half = pw & 1;
     const int k = a.k;
     // lane = 16-byte chunk of a rating (lanes 0..KT-1: factors, lane KT: the rating value).
     // Offsets of that chunk for the four values of r % 4 (the swizzle phase); + (r / 4) * 512.
@@ -233,94 +243,123 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
       oh4[j] = tc_chunk_offset(j, 4 * min(lane, NCH - 1));
       ol4[j] = tc_chunk_offset(j, NC + 4 * min(lane, NCH - 1));
     }
+    uint8_t* const sb = stage_base + s_own * Cfg::STAGE_BYTES + half * (HR / 4) * 512;   // this warp's half of the slot
     TcItemIter ix;
     ix.init(a);
+    ix.advance(a, s_own);
     if (loader) {
       // ============================ loaders ============================
-      constexpr int W = STAGES;
-      const int w = warp - 5;
-      ix.advance(a, w);
-      uint32_t g = (uint32_t)w;
-      // lane r: column id and position of rating r of the stage under the iterator
+      // lane r < HR: column id of rating half*HR + r of the stage under the iterator
       auto load_ids = [&](const TcItemIter& x, int& col, uint32_t& vm, int64_t& e0) {
         col = 0;
         e0 = 0;
         bool ok = false;
         if (x.valid(a)) {
-          e0 = x.seg_beg + (int64_t)x.st * kTcStageRows;
-          ok = lane < kTcStageRows && x.st * kTcStageRows + lane < x.seg_len;
+          e0 = x.seg_beg + (int64_t)x.st * kTcStageRows + half * HR;
+          ok = lane < HR && x.st * kTcStageRows + half * HR + lane < x.seg_len;
           if (ok) col = __ldg(a.rows.indx + e0 + lane);
         }
         vm = __ballot_sync(0xffffffffu, ok);
       };
-      auto issue = [&](uint32_t gg, int col, uint32_t vm, int64_t e0) {
-        const uint32_t s = gg % STAGES, ph = (gg / STAGES) & 1u;
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);
-        uint8_t* sb = stage_base + s * Cfg::STAGE_BYTES;
-        const float* src_lane = a.fixed + 4 * lane;
-        const bool lane_ok = lane < KT && 4 * lane < k;
+      const float* src_lane = a.fixed + 4 * lane;
+      const bool lane_ok = lane < KT && 4 * lane < k;
+      const uint32_t val_off = tc_chunk_offset(lane & (HR - 1), 4 * KT);
+      auto issue = [&](uint32_t use, int col, uint32_t vm, int64_t e0) {
+        mbar_wait(empty0 + 8 * s_own, (use & 1u) ^ 1u);
 #pragma unroll
-        for (int r = 0; r < kTcStageRows; ++r) {
+        for (int r = 0; r < HR; ++r) {
           const int c = __shfl_sync(0xffffffffu, col, r);
           const bool ok = ((vm >> r) & 1u) && lane_ok;
           if (lane < KT) cp_async16(sb + oh4[r & 3] + (r >> 2) * 512, src_lane + (size_t)c * k, ok ? 16 : 0);
         }
-        if (lane < kTcStageRows) {   // the rating values of the stage: lane r -> column KP of rating r, (val, 0, 0, 0)
+        if (lane < HR) {   // the rating values: lane r -> column KP of rating r, (val, 0, 0, 0)
           const bool ok = (vm >> lane) & 1u;
-          cp_async4(sb + tc_chunk_offset(lane, 4 * KT), a.rows.vals + (ok ? e0 + lane : 0), ok ? 4 : 0);
+          cp_async4(sb + val_off, a.rows.vals + (ok ? e0 + lane : 0), ok ? 4 : 0);
         }
         // this lane's arrival on the stage's raw barrier fires when its copies have landed
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(raw0 + 8 * s) : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(raw0 + 8 * s_own) : "memory");
       };
+      // L2 prefetch of the rows this warp will gather kTcPrefetchUses ring cycles from now: the bytes in
+      // flight against HBM latency are no longer capped by the ring's shared memory (6 x 32 ratings x 400 B).
+      // Lane l asks for 128-byte line (l >> 4) and (l >> 4) + 2 of rating l & 15: a 400-byte row that starts
+      // on a 16-byte boundary touches exactly the 4 lines at +0, +128, +256, +384.
+      const bool do_pf = a.prefetch != 0;
+      TcItemIter px = ix;
+      if (do_pf) px.advance(a, kTcPrefetchUses * STAGES);
+      auto load_pf_ids = [&](const TcItemIter& x, int& col) {
+        col = -1;
+        if (x.valid(a)) {
+          const int rr = half * HR + (lane & (HR - 1));
+          if (x.st * kTcStageRows + rr < x.seg_len)
+            col = __ldg(a.rows.indx + x.seg_beg + (int64_t)x.st * kTcStageRows + rr);
+        }
+      };
+      auto prefetch_rows = [&](int col) {
+        if (col >= 0) {
+          const char* p = reinterpret_cast<const char*>(a.fixed + (size_t)col * k) + (lane >> 4) * 128;
+          if ((lane >> 4) * 128 < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+          if ((lane >> 4) * 128 + 256 < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p + 256));
+        }
+      };
+      int pcol = -1;
+      if (do_pf) load_pf_ids(px, pcol);
       // two register sets (A/B): the ids of the warp's next stage are requested before the current
       // stage is issued and are never moved while the load is outstanding
       int colA, colB;
       uint32_t vmA, vmB;
       int64_t eA, eB;
+      uint32_t use = 0;
       load_ids(ix, colA, vmA, eA);
       while (ix.valid(a)) {
-        ix.advance(a, W);
+        ix.advance(a, STAGES);
         load_ids(ix, colB, vmB, eB);
-        issue(g, colA, vmA, eA);
-        g += W;
+        if (do_pf) {
+          prefetch_rows(pcol);
+          px.advance(a, STAGES);
+          load_pf_ids(px, pcol);
+        }
+        issue(use++, colA, vmA, eA);
         if (!ix.valid(a)) break;
-        ix.advance(a, W);
+        ix.advance(a, STAGES);
         load_ids(ix, colA, vmA, eA);
-        issue(g, colB, vmB, eB);
-        g += W;
+        if (do_pf) {
+          prefetch_rows(pcol);
+          px.advance(a, STAGES);
+          load_pf_ids(px, pcol);
+        }
+        issue(use++, colB, vmB, eB);
       }
       cp_async_wait<0>();
     } else {
       // ============================ splitters ============================
-      constexpr int W = STAGES;
-      const int w = warp - 5 - STAGES;
       const bool mask_head = (a.variant & 16u) != 0;
-      ix.advance(a, w);
-      for (uint32_t g = (uint32_t)w; ix.valid(a); g += W, ix.advance(a, W)) {
-        const uint32_t s = g % STAGES, ph = (g / STAGES) & 1u;
-        mbar_wait(raw0 + 8 * s, ph);
-        uint8_t* sb = stage_base + s * Cfg::STAGE_BYTES;
+      for (uint32_t use = 0; ix.valid(a); ++use, ix.advance(a, STAGES)) {
+        mbar_wait(raw0 + 8 * s_own, use & 1u);
         if (lane < NCH) {
 #pragma unroll
-          for (int r = 0; r < kTcStageRows; ++r) {
-            uint8_t* ph_ = sb + oh4[r & 3] + (r >> 2) * 512;
-            const float4 v = *reinterpret_cast<const float4*>(ph_);
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            l.x = v.x - h.x;
-            l.y = v.y - h.y;
-            l.z = v.z - h.z;
-            l.w = v.w - h.w;
-            if (mask_head) *reinterpret_cast<float4*>(ph_) = h;
-            *reinterpret_cast<float4*>(sb + ol4[r & 3] + (r >> 2) * 512) = l;
+          for (int r0 = 0; r0 < HR; r0 += 4) {
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(sb + oh4[j] + (r0 >> 2) * 512);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 h, l;
+              h.x = __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u);
+              h.y = __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u);
+              h.z = __uint_as_float(__float_as_uint(v[j].z) & 0xFFFFE000u);
+              h.w = __uint_as_float(__float_as_uint(v[j].w) & 0xFFFFE000u);
+              l.x = v[j].x - h.x;
+              l.y = v[j].y - h.y;
+              l.z = v[j].z - h.z;
+              l.w = v[j].w - h.w;
+              if (mask_head) *reinterpret_cast<float4*>(sb + oh4[j] + (r0 >> 2) * 512) = h;
+              *reinterpret_cast<float4*>(sb + ol4[j] + (r0 >> 2) * 512) = l;
+            }
           }
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(full0 + 8 * s);
+        if (lane == 0) mbar_arrive(full0 + 8 * s_own);
       }
     }
   } else if (warp == 4) {

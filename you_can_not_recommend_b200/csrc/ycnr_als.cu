@@ -8,7 +8,9 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "als_kernels.cuh"
@@ -65,66 +67,16 @@ struct DevBuf {
 };
 
 // ---- row classification -------------------------------------------------------------
-constexpr int kDualBins = 6;  // MT_MAX = 4, 8, 12, 16, 20, 24  (n <= 16 .. 96)
+constexpr int kDualBins = 24;  // one bin per tile-row count mt = ceil(n / 4), n <= 96
 constexpr int kMaxChunks = 8;
 constexpr int kMinItemsPerChunk = 4 * 148;   // a persistent Gram launch needs a few items per SM
 
-struct WorkPlan {
-  // host-side lists (indices into the row list)
-  std::vector<int32_t> dual[kDualBins];
-  std::vector<int32_t> fused;
-  std::vector<int32_t> multi, multi_first_item, multi_n_items, multi_len;
-  std::vector<int32_t> item_row, item_off;
-  int64_t ratings_dual[kDualBins] = {0};
-  int64_t ratings_fused = 0, ratings_multi = 0;
+struct PlanCfg {
+  int dual_max, split_cols, fused_max;
 };
 
-void classify(const int32_t* row_len, int n_rows, int dual_max, int split_cols, int fused_max, WorkPlan& w) {
-  for (int r = 0; r < n_rows; ++r) {
-    const int n = row_len[r];
-    if (n <= 0) continue;  // Q2 degenerate row (A = 0 upstream): skipped, see DESIGN.md
-    if (n <= dual_max) {
-      const int b = (n - 1) / 16;
-      w.dual[b].push_back(r);
-      w.ratings_dual[b] += n;
-    } else if (n <= split_cols && n <= fused_max) {
-      w.fused.push_back(r);
-      w.ratings_fused += n;
-    } else {
-      w.multi.push_back(r);
-      w.multi_first_item.push_back((int32_t)w.item_row.size());
-      int cnt = 0;
-      for (int off = 0; off < n; off += split_cols) {
-        w.item_row.push_back(r);
-        w.item_off.push_back(off);
-        ++cnt;
-      }
-      w.multi_n_items.push_back(cnt);
-      w.multi_len.push_back(n);
-      w.ratings_multi += n;
-    }
-  }
-  // longest rows first inside every launch (ties: list order).  Dual rows have at most 16 distinct
-  // lengths per bin: a stable counting sort, O(rows) — this runs per portion on the e2e path.
-  auto by_len_desc = [&](int32_t a, int32_t b) { return row_len[a] != row_len[b] ? row_len[a] > row_len[b] : a < b; };
-  std::vector<int32_t> tmp;
-  for (int b = 0; b < kDualBins; ++b) {
-    auto& d = w.dual[b];
-    if (d.size() < 2) continue;
-    const int hi = 16 * (b + 1);          // lengths of this bin: hi-15 .. hi
-    size_t cnt[17] = {0};
-    for (int32_t r : d) cnt[hi - row_len[r] + 1]++;
-    for (int i = 1; i <= 16; ++i) cnt[i] += cnt[i - 1];
-    tmp.resize(d.size());
-    for (int32_t r : d) tmp[cnt[hi - row_len[r]]++] = r;
-    d.swap(tmp);
-  }
-  std::sort(w.fused.begin(), w.fused.end(), by_len_desc);
-}
-
-// Device-resident plan: one packed int32 array + offsets
+// Device-resident plan: one packed int32 array (row indices per kernel class) + offsets into it
 struct DevPlan {
-  int32_t* base = nullptr;  // not owned when it lives in a staging slot
   int n_dual[kDualBins] = {0};
   size_t off_dual[kDualBins] = {0};
   int n_fused = 0, n_multi = 0, n_items = 0;
@@ -140,51 +92,92 @@ struct DevPlan {
   int64_t chunk_ratings[kMaxChunks] = {0};
 };
 
-size_t plan_words(const WorkPlan& w) {
-  size_t n = 0;
-  for (auto& d : w.dual) n += d.size();
-  n += w.fused.size() + 3 * w.multi.size() + 2 * w.item_row.size();
-  return n;
+// Two passes over the row lengths (len[r * stride]), no allocation, no per-row container work: this runs
+// per portion on the e2e path, where the host has to stay ahead of the GPU.
+//   n <= 0 ............ Q2 degenerate row (A = 0 upstream): skipped, see DESIGN.md
+//   n <= dual_max ..... dual bin (n - 1) / 4
+//   n <= fused_max .... fused primal row (FFMA path only)
+//   otherwise ......... split row: ceil(n / split_cols) work items for the Gram kernels
+void plan_count(const int32_t* len, int stride, int n_rows, const PlanCfg& cfg, DevPlan& p) {
+  p = DevPlan();
+  for (int r = 0; r < n_rows; ++r) {
+    const int n = len[(size_t)r * stride];
+    if (n <= 0) continue;
+    if (n <= cfg.dual_max) {
+      const int b = (n - 1) >> 2;
+      p.n_dual[b]++;
+      p.ratings_dual[b] += n;
+    } else if (n <= cfg.split_cols && n <= cfg.fused_max) {
+      p.n_fused++;
+      p.ratings_fused += n;
+    } else {
+      p.n_multi++;
+      p.n_items += (n + cfg.split_cols - 1) / cfg.split_cols;
+      p.ratings_multi += n;
+    }
+  }
+  size_t o = 0;
+  for (int b = 0; b < kDualBins; ++b) { p.off_dual[b] = o; o += p.n_dual[b]; }
+  p.off_fused = o;        o += p.n_fused;
+  p.off_multi = o;        o += p.n_multi;
+  p.off_multi_first = o;  o += p.n_multi;
+  p.off_multi_n = o;      o += p.n_multi;
+  p.off_item_row = o;     o += p.n_items;
+  p.off_item_off = o;     o += p.n_items;
+  p.words = o;
 }
 
-void pack_plan(const WorkPlan& w, int32_t* host, DevPlan& p, int max_chunks) {
-  size_t o = 0;
-  auto put = [&](const std::vector<int32_t>& v, size_t& off) {
-    off = o;
-    if (!v.empty()) memcpy(host + o, v.data(), v.size() * sizeof(int32_t));
-    o += v.size();
-  };
-  for (int b = 0; b < kDualBins; ++b) {
-    put(w.dual[b], p.off_dual[b]);
-    p.n_dual[b] = (int)w.dual[b].size();
-    p.ratings_dual[b] = w.ratings_dual[b];
+void plan_fill(const int32_t* len, int stride, int n_rows, const PlanCfg& cfg, DevPlan& p, int32_t* out, int max_chunks) {
+  size_t cur[kDualBins];
+  for (int b = 0; b < kDualBins; ++b) cur[b] = p.off_dual[b];
+  size_t cf = p.off_fused;
+  int m = 0, it = 0;
+  int32_t* multi = out + p.off_multi;
+  int32_t* mfirst = out + p.off_multi_first;
+  int32_t* mn = out + p.off_multi_n;
+  int32_t* irow = out + p.off_item_row;
+  int32_t* ioff = out + p.off_item_off;
+  for (int r = 0; r < n_rows; ++r) {
+    const int n = len[(size_t)r * stride];
+    if (n <= 0) continue;
+    if (n <= cfg.dual_max) {
+      out[cur[(n - 1) >> 2]++] = r;
+    } else if (n <= cfg.split_cols && n <= cfg.fused_max) {
+      out[cf++] = r;
+    } else {
+      multi[m] = r;
+      mfirst[m] = it;
+      int cnt = 0;
+      for (int off = 0; off < n; off += cfg.split_cols, ++cnt) {
+        irow[it] = r;
+        ioff[it] = off;
+        ++it;
+      }
+      mn[m] = cnt;
+      ++m;
+    }
   }
-  put(w.fused, p.off_fused);
-  put(w.multi, p.off_multi);
-  put(w.multi_first_item, p.off_multi_first);
-  put(w.multi_n_items, p.off_multi_n);
-  put(w.item_row, p.off_item_row);
-  put(w.item_off, p.off_item_off);
-  p.n_fused = (int)w.fused.size();
-  p.n_multi = (int)w.multi.size();
-  p.n_items = (int)w.item_row.size();
-  p.ratings_fused = w.ratings_fused;
-  p.ratings_multi = w.ratings_multi;
-  p.words = o;
+  if (p.n_fused > 1) {   // longest rows first inside the launch (ties: list order)
+    int32_t* f = out + p.off_fused;
+    std::sort(f, f + p.n_fused, [&](int32_t x, int32_t y) {
+      const int lx = len[(size_t)x * stride], ly = len[(size_t)y * stride];
+      return lx != ly ? lx > ly : x < y;
+    });
+  }
   // chunk cuts at equal cumulative ratings
-  const int nm = (int)w.multi.size();
-  int chunks = (int)std::min<int64_t>(std::min(kMaxChunks, max_chunks), (int64_t)w.item_row.size() / kMinItemsPerChunk);
+  const int nm = p.n_multi;
+  int chunks = (int)std::min<int64_t>(std::min(kMaxChunks, max_chunks), (int64_t)p.n_items / kMinItemsPerChunk);
   if (chunks < 2) chunks = 1;
   p.n_chunks = chunks;
   p.chunk_row[0] = 0;
   p.chunk_item[0] = 0;
   int64_t acc = 0, done = 0;
   int c = 1;
-  for (int m = 0; m < nm && c < chunks; ++m) {
-    acc += w.multi_len[m];
-    if (acc >= w.ratings_multi * c / chunks) {
-      p.chunk_row[c] = m + 1;
-      p.chunk_item[c] = w.multi_first_item[m] + w.multi_n_items[m];
+  for (int q = 0; q < nm && c < chunks; ++q) {
+    acc += len[(size_t)multi[q] * stride];
+    if (acc >= p.ratings_multi * c / chunks) {
+      p.chunk_row[c] = q + 1;
+      p.chunk_item[c] = mfirst[q] + mn[q];
       p.chunk_ratings[c - 1] = acc - done;
       done = acc;
       ++c;
@@ -192,8 +185,8 @@ void pack_plan(const WorkPlan& w, int32_t* host, DevPlan& p, int max_chunks) {
   }
   for (; c <= chunks; ++c) {   // last cut (and any cut the loop did not reach)
     p.chunk_row[c] = nm;
-    p.chunk_item[c] = (int)w.item_row.size();
-    if (c - 1 < kMaxChunks) { p.chunk_ratings[c - 1] = w.ratings_multi - done; done = w.ratings_multi; }
+    p.chunk_item[c] = p.n_items;
+    if (c - 1 < kMaxChunks) { p.chunk_ratings[c - 1] = p.ratings_multi - done; done = p.ratings_multi; }
   }
 }
 
@@ -261,6 +254,10 @@ struct ycnr_ctx {
   int step_type = -1;
   double rmse_shift = 0.0;
   std::vector<std::pair<int32_t, int32_t>> solved_ranges;  // [first,last] row ids per portion
+  // YCNR_TRACE=1: host-side time of the per-portion path, printed per step to stderr
+  bool trace = false;
+  double t_parse = 0, t_slot_wait = 0, t_copy_issue = 0, t_launch = 0;
+  int t_portions = 0;
   // profiling
   std::vector<ProfRec> prof_open;
   std::vector<cudaEvent_t> ev_pool;
@@ -330,6 +327,7 @@ int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int item_from, int n
     t.split_cols = pa.split_cols;
     t.partial = pa.partial + (size_t)item_from * NTILES * 16;
     t.variant = (uint32_t)c->opts.tc_variant;
+    t.prefetch = pa.fixed_bytes > ((size_t)48 << 20) ? 1 : 0;
     const size_t smem = gram_tc_smem_bytes<KT>();
     static bool configured = false;
     if (!configured) {
@@ -363,9 +361,10 @@ int launch_primal_kt(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p
     a.work = plan_base + p.off_multi;
     a.row_first_item = plan_base + p.off_multi_first;
     a.row_n_items = plan_base + p.off_multi_n;
-    if (c->use_tc && p.n_chunks > 1) {
-      // Gram of chunk i+1 (tensor pipe / shared memory) overlaps reduce+solve of chunk i (FFMA, barrier
-      // latency) on the aux stream; both kernels fit on an SM together.  The caller joins the aux stream.
+    if (c->use_tc && c->opts.solve_chunks >= 0) {
+      // reduce+solve (FFMA, ~50 % barrier stalls: the serial pivot chain) runs on the aux stream, under
+      // whatever the main stream launches next: the dual kernels of the same half-step, and — with
+      // solve_chunks > 1 — the Gram of the next chunk.  The caller joins the aux stream.
       for (int ch = 0; ch < p.n_chunks; ++ch) {
         const int i0 = p.chunk_item[ch], i1 = p.chunk_item[ch + 1];
         const int m0 = p.chunk_row[ch], m1 = p.chunk_row[ch + 1];
@@ -408,13 +407,26 @@ int launch_primal(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p, c
   return fail("factorsCount %d > 128 is not supported by this build", k);
 }
 
+// threads per CTA for systems of mt tile rows: room for a 2..8-way K-split of the Gram sweep while
+// the systems are small (mt <= 8), exactly the tile set (rounded to warps) above that
+// (measured on B200, MAL byUser: the K-split pays for mt <= 8 — 7.2 ms against 8.5 ms for those rows —
+//  and costs occupancy above that)
+constexpr int dual_nt(int mt) {
+  if (mt <= 4) return 32;
+  if (mt <= 6) return 64;
+  if (mt <= 8) return 96;
+  return (ycnr::dual_ntl(mt) + 31) & ~31;
+}
+
 template <int MT_MAX, int NT>
 int launch_dual_bin(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t ratings, const int32_t* work) {
   using namespace ycnr;
   if (count <= 0) return 0;
   DualArgs a = base;
   a.work = work;
-  const size_t smem = ((size_t)4 * MT_MAX * a.pitch + (MT_MAX + 1) * 16 + 16 * MT_MAX + 8 * MT_MAX) * sizeof(float);
+  int red = 0;
+  for (int mt = 1; mt <= MT_MAX; ++mt) red = std::max(red, dual_red_floats(mt, NT));
+  const size_t smem = ((size_t)4 * MT_MAX * a.pitch + (MT_MAX + 1) * 16 + 16 * MT_MAX + 8 * MT_MAX + red) * sizeof(float);
   static size_t configured = 0;  // per instantiation
   if (smem > 48 * 1024 && smem > configured) {
     CU(cudaFuncSetAttribute(als_dual_kernel<MT_MAX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -424,6 +436,16 @@ int launch_dual_bin(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t 
   als_dual_kernel<MT_MAX, NT><<<count, NT, smem, c->stream>>>(a);
   CU(cudaGetLastError());
   return 0;
+}
+
+template <int... B>
+int launch_dual_bins(ycnr_ctx* c, const ycnr::DualArgs& d, const DevPlan& p, const int32_t* plan_base,
+                     std::integer_sequence<int, B...>) {
+  int rc = 0;
+  ((rc = rc ? rc
+            : launch_dual_bin<B + 1, dual_nt(B + 1)>(c, d, p.n_dual[B], p.ratings_dual[B], plan_base + p.off_dual[B])),
+   ...);
+  return rc;
 }
 
 int dual_pitch(int k) {
@@ -447,6 +469,7 @@ int run_als(ycnr_ctx* c, int step_type, const RowsView& view, const DevPlan& p, 
   ycnr::PrimalArgs a{};
   a.rows = view;
   a.fixed = c->d_fac[fixed];
+  a.fixed_bytes = (size_t)c->fac_rows[fixed] * c->k * sizeof(float);
   a.k = c->k;
   a.lambda = lambda;
   a.dst = d.dst;
@@ -455,12 +478,7 @@ int run_als(ycnr_ctx* c, int step_type, const RowsView& view, const DevPlan& p, 
   CU(cudaEventRecord(c->chunk_ev[kMaxChunks], c->stream));
   CU(cudaStreamWaitEvent(c->aux_stream, c->chunk_ev[kMaxChunks], 0));   // aux starts after everything queued so far
   OK(launch_primal(c, a, p, plan_base));
-  OK((launch_dual_bin<4, 32>(c, d, p.n_dual[0], p.ratings_dual[0], plan_base + p.off_dual[0])));
-  OK((launch_dual_bin<8, 64>(c, d, p.n_dual[1], p.ratings_dual[1], plan_base + p.off_dual[1])));
-  OK((launch_dual_bin<12, 96>(c, d, p.n_dual[2], p.ratings_dual[2], plan_base + p.off_dual[2])));
-  OK((launch_dual_bin<16, 160>(c, d, p.n_dual[3], p.ratings_dual[3], plan_base + p.off_dual[3])));
-  OK((launch_dual_bin<20, 256>(c, d, p.n_dual[4], p.ratings_dual[4], plan_base + p.off_dual[4])));
-  OK((launch_dual_bin<24, 352>(c, d, p.n_dual[5], p.ratings_dual[5], plan_base + p.off_dual[5])));
+  OK(launch_dual_bins(c, d, p, plan_base, std::make_integer_sequence<int, kDualBins>{}));
   if (c->aux_pending) {
     CU(cudaEventRecord(c->chunk_ev[kMaxChunks + 1], c->aux_stream));
     CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[kMaxChunks + 1], 0));
@@ -522,39 +540,40 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
   const int R = rows[0];
   if (R < 0) return fail("portion header: negative row count");
   s.n_rows = R;
-  std::vector<int32_t> ids(R), len(R);
-  std::vector<int64_t> start(R);
+  const int32_t* hdr_len = rows + 2;   // (rowId, n) pairs: lengths at stride 2
   int64_t off = 0;
   for (int r = 0; r < R; ++r) {
-    ids[r] = rows[1 + 2 * r];
-    len[r] = rows[1 + 2 * r + 1];
-    if (len[r] < 0) return fail("portion header: negative cols");
-    start[r] = off;
-    off += len[r];
+    const int n = hdr_len[2 * (size_t)r];
+    if (n < 0) return fail("portion header: negative cols");
+    off += n;
   }
   s.ratings = off;
-  if (R > 0) { s.first_row = ids[0]; s.last_row = ids[R - 1]; }
-  WorkPlan w;
-  if (with_plan) classify(len.data(), R, c->dual_max, c->split_cols, c->fused_max, w);
-  const size_t pw = with_plan ? plan_words(w) : 0;
-  // layout (8-byte aligned sections): start[R] i64 | sums f64 [2R+3] | ids[R] | len[R] | pfirst[2] | plan | indx | vals
+  if (R > 0) { s.first_row = rows[1]; s.last_row = rows[1 + 2 * (size_t)(R - 1)]; }
+  const PlanCfg cfg{c->dual_max, c->split_cols, c->fused_max};
+  if (with_plan) plan_count(hdr_len, 2, R, cfg, s.plan);
+  const size_t pw = with_plan ? s.plan.words : 0;
+  // layout (16-byte aligned sections): start[R] i64 | ids[R] | len[R] | pfirst[2] | plan | indx | vals
+  //                                      | sums f64 [2R+3] (device only: RMSE scratch, never copied)
   auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
   size_t o_start = 0;
-  size_t o_sums = al(o_start + (size_t)R * 8);
-  size_t o_ids = al(o_sums + (size_t)(2 * R + 3) * 8);
+  size_t o_ids = al(o_start + (size_t)R * 8);
   size_t o_len = al(o_ids + (size_t)R * 4);
   size_t o_pf = al(o_len + (size_t)R * 4);
   size_t o_plan = al(o_pf + 8);
   size_t o_indx = al(o_plan + pw * 4);
   size_t o_vals = al(o_indx + (size_t)off * 4);
   size_t total = al(o_vals + (size_t)off * 4);
+  size_t o_sums = total;
+  size_t dev_total = with_plan ? total : al(o_sums + (size_t)(2 * R + 3) * 8);
 
   Slot& sl = c->slots[c->next_slot];
   c->next_slot = (c->next_slot + 1) % kSlots;
+  const double tw0 = now_ms();
   if (sl.pending) {
     CU(cudaEventSynchronize(sl.done));
     sl.pending = false;
   }
+  c->t_slot_wait += now_ms() - tw0;
   if (!sl.done) CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
   if (!sl.solved) CU(cudaEventCreateWithFlags(&sl.solved, cudaEventDisableTiming));
   // ratings that already sit in page-locked caller memory are DMA'd from there
@@ -574,18 +593,29 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
     CU(cudaMallocHost(&sl.host, want));
     sl.host_cap = want;
   }
-  OK(sl.dev.ensure(total));
+  OK(sl.dev.ensure(dev_total));
   char* h = (char*)sl.host;
-  if (R) {
-    memcpy(h + o_start, start.data(), (size_t)R * 8);
-    memcpy(h + o_ids, ids.data(), (size_t)R * 4);
-    memcpy(h + o_len, len.data(), (size_t)R * 4);
+  const double tp0 = now_ms();
+  {   // header -> row arrays, written in place in the page-locked slot
+    int64_t* h_start = (int64_t*)(h + o_start);
+    int32_t* h_ids = (int32_t*)(h + o_ids);
+    int32_t* h_len = (int32_t*)(h + o_len);
+    int64_t run = 0;
+    for (int r = 0; r < R; ++r) {
+      const int32_t id = rows[1 + 2 * (size_t)r], n = rows[2 + 2 * (size_t)r];
+      h_ids[r] = id;
+      h_len[r] = n;
+      h_start[r] = run;
+      run += n;
+    }
+    if (with_plan) plan_fill(h_len, 1, R, cfg, s.plan, (int32_t*)(h + o_plan), c->opts.solve_chunks);
   }
   int32_t pf[2] = {0, R};
   memcpy(h + o_pf, pf, 8);
-  if (with_plan) pack_plan(w, (int32_t*)(h + o_plan), s.plan, c->opts.solve_chunks);
+  const double tp1 = now_ms();
+  c->t_parse += tp1 - tp0;
+  c->t_portions++;
   char* d = (char*)sl.dev.p;
-  // (the f64 scratch section is not meaningful on the host side, but it sits inside the range)
   if (direct) {
     CU(cudaMemcpyAsync(d, h, o_indx, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaMemcpyAsync(d + o_indx, indx, (size_t)off * 4, cudaMemcpyHostToDevice, c->copy_stream));
@@ -599,6 +629,7 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
   }
   CU(cudaEventRecord(c->copied, c->copy_stream));
   CU(cudaStreamWaitEvent(c->stream, c->copied, 0));
+  c->t_copy_issue += now_ms() - tp1;
   // Unregistered caller buffers were copied into the slot above and may be refilled once we return.
   // Regions registered with ycnr_host_register are a portion CACHE (usePortionsCache): they are DMA'd
   // asynchronously and must stay unmodified until the step ends (ycnr_end_train_step / the return of
@@ -681,6 +712,7 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
               (o->gram_path == YCNR_GRAM_AUTO && (c->k & 3) == 0 && c->k <= 124 && c->k >= 16);
   c->fused_max = c->use_tc ? (o->tc_min_cols > 0 ? o->tc_min_cols - 1 : 0) : c->split_cols;
   c->num_sms = prop.multiProcessorCount;
+  c->trace = getenv("YCNR_TRACE") != nullptr;
   c->fac_rows[0] = o->total_users;
   c->fac_rows[1] = o->total_items;
   CU(cudaSetDevice(o->device));
@@ -839,7 +871,9 @@ int ycnr_als_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, cons
   StagedPortion s;
   OK(stage_portion(c, rows, indx, vals, true, s));
   if (s.n_rows > 0) {
+    const double tl0 = now_ms();
     OK(run_als(c, c->step_type, s.view, s.plan, s.plan_base));
+    c->t_launch += now_ms() - tl0;
     const int solved = c->step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
     if (c->h_fac[solved] && c->h_registered[solved]) {
       // the portion's row-id range goes back to the host segment on its own stream as soon as its kernels
@@ -886,7 +920,16 @@ int ycnr_end_train_step(ycnr_ctx* c) {
       i = j;
     }
   }
+  const double ts0 = now_ms();
   CU(cudaStreamSynchronize(c->stream));
+  const double ts1 = now_ms();
+  if (c->trace) {
+    fprintf(stderr, "[ycnr trace] step %d: %d portions, host parse %.2f ms, slot wait %.2f ms, copy issue %.2f ms, "
+            "launch %.2f ms, final sync %.2f ms\n", c->step_type, c->t_portions, c->t_parse, c->t_slot_wait,
+            c->t_copy_issue, c->t_launch, ts1 - ts0);
+  }
+  c->t_parse = c->t_slot_wait = c->t_copy_issue = c->t_launch = 0;
+  c->t_portions = 0;
   if (c->d2h_pending) {
     CU(cudaStreamSynchronize(c->d2h_stream));
     c->d2h_pending = false;
@@ -1025,10 +1068,10 @@ int ycnr_rowset_create(ycnr_ctx* c, int32_t step_type, int32_t n_rows, const int
   rs.view.vals = (const float*)(dr + o_vals);
   std::vector<int32_t> packed;
   if (!rmse) {
-    WorkPlan w;
-    classify(row_len, n_rows, c->dual_max, c->split_cols, c->fused_max, w);
-    packed.resize(plan_words(w) + 1);
-    pack_plan(w, packed.data(), rs.dplan, c->opts.solve_chunks);
+    const PlanCfg cfg{c->dual_max, c->split_cols, c->fused_max};
+    plan_count(row_len, 1, n_rows, cfg, rs.dplan);
+    packed.resize(rs.dplan.words + 1);
+    plan_fill(row_len, 1, n_rows, cfg, rs.dplan, packed.data(), c->opts.solve_chunks);
     OK(rs.plan.ensure(packed.size() * 4));
     CU(cudaMemcpyAsync(rs.plan.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, c->stream));
   } else {
