@@ -83,10 +83,9 @@ typedef struct ycnr_options {
   int32_t tc_min_cols;          /* TC path: rows with at least this many ratings (and more than
                                    dual_max_cols) take the tensor-core Gram; 0 = all of them */
   int32_t tc_variant;           /* diagnostics only, keep 0 (16: raw fp32 in the TF32 head columns) */
-  int32_t solve_chunks;         /* 0/1 (default): the reduce+solve of the split rows runs on a second stream under the
-                                   dual kernels of the same half-step; > 1: additionally cut the split rows into this
-                                   many groups (<= 8), reduce+solve of group i under the Gram of group i+1;
-                                   < 0: everything on one stream */
+  int32_t solve_chunks;         /* > 1: cut the split rows of a half-step into this many groups (<= 8) and run the
+                                   reduce+solve of group i on a second stream under the Gram of group i+1
+                                   (measured: no gain on B200, default 0 = stream order) */
   int32_t reserved[1];
 } ycnr_options;
 

@@ -193,6 +193,41 @@ def test_rmse_portion_vs_oracle(k):
     ctx.close()
 
 
+@pytest.mark.parametrize("registered", [False, True])
+def test_rmse_portion_large_header_device_unpack(registered):
+    """The RMSE path unpacks the raw header on the device (three-kernel prefix sum over the row lengths):
+    70 000 rows = 35 scan blocks, ragged lengths incl. zeros, with plain and with page-locked (cached)
+    portion buffers.  Counts are exact, sums match the oracle to fp64 summation-order noise."""
+    k, users, items = 16, 70_000, 500
+    rng = np.random.default_rng(11)
+    U = rng.normal(0, 0.4, (users, k)).astype(np.float32)
+    V = rng.normal(0, 0.4, (items, k)).astype(np.float32)
+    lens = rng.integers(0, 7, users).astype(np.int32)
+    lens[::997] = 40
+    R = users
+    rows = np.zeros(2 * R + 1, np.int32)
+    rows[0] = R
+    rows[1::2] = np.arange(R, dtype=np.int32)
+    rows[2::2] = lens
+    nnz = int(lens.sum())
+    indx = rng.integers(0, items, nnz + 1).astype(np.int32)
+    vals = rng.integers(1, 6, nnz + 1).astype(np.float32)
+    want = oracle.rmse_portion(rows, indx, vals, U.astype(np.float64), V.astype(np.float64), 0.25)
+    ctx = native.Context(k, users, items)
+    ctx.attach_factors(U, V)
+    if registered:
+        for a in (rows, indx, vals):
+            ctx.host_register(a)
+    ctx.start_calc_rmse(native.RMSE_VALIDATE, 0.25)
+    for _ in range(2):                               # slot reuse
+        info = ctx.rmse_portion(rows, indx, vals)
+        assert info.r_cnt == want[1] == nnz
+        assert info.rows_from == 0 and info.rows_cnt == R and info.ratings_in_portion == nnz
+        assert abs(info.r_sum_diff2 - want[0]) <= 1e-5 * want[0]
+        assert abs(info.r_sum - want[2]) <= 1e-5 * abs(want[2]) + 1e-6
+    ctx.close()
+
+
 @pytest.mark.parametrize("bulk", [False, True])
 def test_c1_ten_iteration_trajectory(bulk):
     """BASELINE configs[0]: ML-100k shape, k=20, 85/10/5, 10 iterations through the worker interface."""

@@ -15,6 +15,7 @@
 
 #include "als_kernels.cuh"
 #include "gram_tc.cuh"
+#include "portion_kernels.cuh"
 #include "rmse_kernels.cuh"
 
 namespace {
@@ -361,10 +362,10 @@ int launch_primal_kt(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p
     a.work = plan_base + p.off_multi;
     a.row_first_item = plan_base + p.off_multi_first;
     a.row_n_items = plan_base + p.off_multi_n;
-    if (c->use_tc && c->opts.solve_chunks >= 0) {
-      // reduce+solve (FFMA, ~50 % barrier stalls: the serial pivot chain) runs on the aux stream, under
-      // whatever the main stream launches next: the dual kernels of the same half-step, and — with
-      // solve_chunks > 1 — the Gram of the next chunk.  The caller joins the aux stream.
+    if (c->use_tc && p.n_chunks > 1) {
+      // optional (solve_chunks > 1): reduce+solve of chunk i on the aux stream under the Gram of chunk i+1.
+      // Measured on B200 (MAL): no gain — 56.5 ms per iteration with the solve overlapped against 55.7 ms
+      // in stream order; both kernels compete for the same issue slots — so it is off by default.
       for (int ch = 0; ch < p.n_chunks; ++ch) {
         const int i0 = p.chunk_item[ch], i1 = p.chunk_item[ch + 1];
         const int m0 = p.chunk_row[ch], m1 = p.chunk_row[ch + 1];
@@ -642,6 +643,115 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
   s.d_sums = (double*)(d + o_sums);
   s.d_pfirst = (const int32_t*)(d + o_pf);
   s.plan_base = (const int32_t*)(d + o_plan);
+  s.slot = &sl;
+  return 0;
+}
+
+// RMSE portions: the raw header is DMA'd and unpacked on the device (portion_kernels.cuh); the host only
+// sums the row lengths (it needs the ratings count to size the copy of indx/vals).
+int stage_rmse_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals, StagedPortion& s) {
+  const int R = rows[0];
+  if (R < 0) return fail("portion header: negative row count");
+  s.n_rows = R;
+  int64_t off = 0;
+  int32_t any_neg = 0;
+  for (int r = 0; r < R; ++r) {
+    const int32_t n = rows[2 + 2 * (size_t)r];
+    any_neg |= n;
+    off += n;
+  }
+  if (any_neg < 0) return fail("portion header: negative cols");
+  s.ratings = off;
+  if (R > 0) { s.first_row = rows[1]; s.last_row = rows[1 + 2 * (size_t)(R - 1)]; }
+  const int nb = (R + ycnr::kUnpackRowsPerBlock - 1) / ycnr::kUnpackRowsPerBlock;
+  // device layout (16-byte aligned sections): pad(4 B) hdr[2R+1] | pfirst[2] | start[R] i64 | ids[R] | len[R]
+  //                                           | block sums i64[nb] | indx | vals | sums f64[2R+3]
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t hdr_bytes = (size_t)(2 * R + 1) * 4;
+  size_t o_hdr = 4;   // hdr[1] (the first (rowId, n) pair) lands on an 8-byte boundary
+  size_t o_pf = al(o_hdr + hdr_bytes);
+  size_t o_start = al(o_pf + 8);
+  size_t o_ids = al(o_start + (size_t)R * 8);
+  size_t o_len = al(o_ids + (size_t)R * 4);
+  size_t o_bs = al(o_len + (size_t)R * 4);
+  size_t o_indx = al(o_bs + (size_t)(nb + 1) * 8);
+  size_t o_vals = al(o_indx + (size_t)off * 4);
+  size_t o_sums = al(o_vals + (size_t)off * 4);
+  size_t dev_total = al(o_sums + (size_t)(2 * R + 3) * 8);
+
+  Slot& sl = c->slots[c->next_slot];
+  c->next_slot = (c->next_slot + 1) % kSlots;
+  if (sl.pending) {
+    CU(cudaEventSynchronize(sl.done));
+    sl.pending = false;
+  }
+  if (!sl.done) CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  if (!sl.solved) CU(cudaEventCreateWithFlags(&sl.solved, cudaEventDisableTiming));
+  auto is_pinned = [&](const void* p, size_t bytes) {
+    const char* q = (const char*)p;
+    for (auto& r : c->pinned)
+      if (q >= r.first && q + bytes <= r.first + r.second) return true;
+    return false;
+  };
+  const bool hdr_direct = is_pinned(rows, hdr_bytes);
+  const bool direct = off > 0 && is_pinned(indx, (size_t)off * 4) && is_pinned(vals, (size_t)off * 4);
+  // staging (page-locked slot memory): pfirst | [hdr] | [indx | vals]
+  const size_t h_pf = 0, h_hdr = 16, h_indx = al(h_hdr + (hdr_direct ? 0 : hdr_bytes));
+  const size_t h_vals = al(h_indx + (direct ? 0 : (size_t)off * 4));
+  const size_t host_need = al(h_vals + (direct ? 0 : (size_t)off * 4));
+  if (host_need > sl.host_cap) {
+    if (sl.host) cudaFreeHost(sl.host);
+    sl.host = nullptr;
+    sl.host_cap = 0;
+    size_t want = host_need + host_need / 4 + 4096;
+    CU(cudaMallocHost(&sl.host, want));
+    sl.host_cap = want;
+  }
+  OK(sl.dev.ensure(dev_total));
+  char* h = (char*)sl.host;
+  char* d = (char*)sl.dev.p;
+  int32_t pf[2] = {0, R};
+  memcpy(h + h_pf, pf, 8);
+  CU(cudaMemcpyAsync(d + o_pf, h + h_pf, 8, cudaMemcpyHostToDevice, c->copy_stream));
+  if (hdr_direct) {
+    CU(cudaMemcpyAsync(d + o_hdr, rows, hdr_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  } else {
+    memcpy(h + h_hdr, rows, hdr_bytes);
+    CU(cudaMemcpyAsync(d + o_hdr, h + h_hdr, hdr_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  if (off) {
+    if (direct) {
+      CU(cudaMemcpyAsync(d + o_indx, indx, (size_t)off * 4, cudaMemcpyHostToDevice, c->copy_stream));
+      CU(cudaMemcpyAsync(d + o_vals, vals, (size_t)off * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    } else {
+      memcpy(h + h_indx, indx, (size_t)off * 4);
+      memcpy(h + h_vals, vals, (size_t)off * 4);
+      CU(cudaMemcpyAsync(d + o_indx, h + h_indx, (size_t)off * 4, cudaMemcpyHostToDevice, c->copy_stream));
+      CU(cudaMemcpyAsync(d + o_vals, h + h_vals, (size_t)off * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    }
+  }
+  CU(cudaEventRecord(c->copied, c->copy_stream));
+  CU(cudaStreamWaitEvent(c->stream, c->copied, 0));
+  const int32_t* d_hdr = (const int32_t*)(d + o_hdr);
+  int64_t* d_bs = (int64_t*)(d + o_bs);
+  if (R > 0) {
+    ProfScope ps(c, YCNR_K_GATHER, R, 0);   // accounted with the data-movement kernels
+    ycnr::header_block_sums_kernel<<<nb, ycnr::kUnpackThreads, 0, c->stream>>>(d_hdr, R, d_bs);
+    ycnr::header_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(d_bs, nb);
+    ycnr::header_unpack_kernel<<<nb, ycnr::kUnpackThreads, 0, c->stream>>>(
+        d_hdr, R, d_bs, (int32_t*)(d + o_ids), (int32_t*)(d + o_len), (int64_t*)(d + o_start));
+    CU(cudaGetLastError());
+    c->prof.launches[YCNR_K_GATHER] += 2;   // three launches in the scope above
+    c->prof.total_launches += 2;
+  }
+  s.view.row_start = (const int64_t*)(d + o_start);
+  s.view.row_ids = (const int32_t*)(d + o_ids);
+  s.view.row_len = (const int32_t*)(d + o_len);
+  s.view.indx = (const int32_t*)(d + o_indx);
+  s.view.vals = (const float*)(d + o_vals);
+  s.d_sums = (double*)(d + o_sums);
+  s.d_pfirst = (const int32_t*)(d + o_pf);
+  s.plan_base = nullptr;
   s.slot = &sl;
   return 0;
 }
@@ -957,7 +1067,7 @@ int ycnr_rmse_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, con
   const double t0 = now_ms();
   OK(set_device(c));
   StagedPortion s;
-  OK(stage_portion(c, rows, indx, vals, false, s));
+  OK(stage_rmse_portion(c, rows, indx, vals, s));
   double sums[3] = {0, 0, 0};
   if (s.n_rows > 0) {
     double* d_portion = s.d_sums + 2 * (size_t)s.n_rows;

@@ -164,6 +164,8 @@ class EmfMaster(EmfBase):
                 hdr[0] = r1 - r0
                 hdr[1::2] = rl.row_ids[r0:r1]
                 hdr[2::2] = rl.row_len[r0:r1]
+                if hdr.nbytes >= (1 << 16):          # big headers are DMA'd straight from the cache too
+                    self.ctx.host_register(hdr)
                 a = int(csr.ptr[0 if p == 0 else pto[p - 1]])
                 b = max(int(csr.ptr[pto[p]]), a + 1) if csr.nnz else a
                 bufs.append({prefix + "Rows": hdr, prefix + "Indx": csr.idx[a:b], prefix + "Vals": csr.vals[a:b],
