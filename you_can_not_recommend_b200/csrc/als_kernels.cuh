@@ -24,6 +24,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef YCNR_DUAL_FFMA2
+#define YCNR_DUAL_FFMA2 1
+#endif
+
 namespace ycnr {
 
 enum { MODE_FUSED = 0, MODE_PARTIAL = 1, MODE_REDUCE = 2 };
@@ -84,7 +88,9 @@ __device__ __forceinline__ void chol4_inverse(float (&d)[4][4]) {
 // On return ysm[0 .. 4*mt) holds the solution.  All threads of the CTA must call.
 // Two barriers per tile column in the factorisation (the owner of the next diagonal tile
 // factors it right after its own trailing update — look-ahead — so nobody waits on a
-// dedicated "factor" phase) and one per tile row in the back substitution.
+// dedicated "factor" phase) and one per tile row in the back substitution.  (A single-warp back
+// substitution over factor tiles staged in shared memory was measured on B200: k x k solves 7.87 -> 7.65 ms,
+// dual rows 20.5 -> 21.2 ms per MAL iteration — its serial latency hurts the small systems; not kept.)
 template <int TPT>
 __device__ __forceinline__ void tile_cholesky_solve(float (&acc)[TPT][4][4], const int (&tI)[TPT],
                                                     const int (&tL)[TPT], int mt, float* panel, float* minv,
@@ -475,6 +481,38 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
     const int tstride = mt * pitch;
     const int CHT = K4 >> 2;
     const int c_beg = 4 * ((g * CHT) / G), c_end = 4 * (((g + 1) * CHT) / G);
+#if YCNR_DUAL_FFMA2
+    // packed FP32 FMA (fma.rn.f32x2, sm_100): the two lanes of a pair accumulate the even and the odd
+    // column pairs of the chunk, so both operands are register pairs exactly as LDS.128 delivered them;
+    // half the FMA issue slots of the scalar loop (ncu: these kernels are issue-bound, 65-72 % issue active
+    // with FFMA only 1/3-1/2 of the instructions)
+    float2 acc2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
+    for (int c = c_beg; c < c_end; c += 4) {
+      float4 av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        av[i] = *reinterpret_cast<const float4*>(ya + i * tstride + c);
+        bv[i] = *reinterpret_cast<const float4*>(yb + i * tstride + c);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 s = acc2[i][j];
+          s = __ffma2_rn(make_float2(av[i].x, av[i].y), make_float2(bv[j].x, bv[j].y), s);
+          s = __ffma2_rn(make_float2(av[i].z, av[i].w), make_float2(bv[j].z, bv[j].w), s);
+          acc2[i][j] = s;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[0][i][j] = acc2[i][j].x + acc2[i][j].y;
+#else
     for (int c = c_beg; c < c_end; c += 4) {
       float4 av[4], bv[4];
 #pragma unroll
@@ -494,6 +532,7 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
           acc[0][i][j] = s;
         }
     }
+#endif
   }
   if (G > 1) {   // uniform over the CTA
     if (g > 0) {

@@ -18,6 +18,10 @@
 #include "portion_kernels.cuh"
 #include "rmse_kernels.cuh"
 
+#ifndef YCNR_REDUCE_TPT
+#define YCNR_REDUCE_TPT 2
+#endif
+
 namespace {
 
 thread_local char g_err[1024] = "";
@@ -390,7 +394,9 @@ int launch_primal_kt(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p
         als_primal_kernel<KT, NT, 1, MODE_PARTIAL><<<p.n_items, NT, 0, c->stream>>>(a);
       }
       ProfScope ps(c, YCNR_K_REDUCE_SOLVE, p.n_multi, 0);
-      als_primal_kernel<KT, NT, 1, MODE_REDUCE><<<p.n_multi, NT, 0, c->stream>>>(a);
+      constexpr int RT = YCNR_REDUCE_TPT;                                   // tiles per thread of the solve
+      constexpr int RNT = (((NTILES + RT - 1) / RT) + 31) & ~31;
+      als_primal_kernel<KT, RNT, RT, MODE_REDUCE><<<p.n_multi, RNT, 0, c->stream>>>(a);
     }
   }
   CU(cudaGetLastError());

@@ -53,6 +53,7 @@ class EmfMaster(EmfBase):
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.fusedPeers = False
+        self.sharedHost = False
         self._ranges = {}
         self.phase_ms = {}
 
@@ -105,6 +106,10 @@ class EmfMaster(EmfBase):
         self.splitDataForTrain()
         if userFactors is not None:
             self.openSharedFactors(userFactors, itemFactors)      # warm start (EmfManager.js:405-457)
+        elif self.world > 1 and not o["gpu"]["bulk"]:
+            # upstream, every worker of a node maps the SAME SysV segments (EmfBase.js:403-412, 430-450) and
+            # writes its own rows into them: one /dev/shm mapping shared by all ranks of the box
+            self._createNodeSharedFactors()
         else:
             self.createSharedFactors()
             self.initSharedFactorsRandom()
@@ -194,6 +199,28 @@ class EmfMaster(EmfBase):
             self.rowlists[step] = (ids, ln, pf)
             self.rowsets[step] = rid
 
+    def _createNodeSharedFactors(self):
+        import os
+        k = self.factorsCount
+        tag = "%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid())
+        self._shm_paths = ["/dev/shm/ycnr_%s_%s" % (tag, n) for n in ("user_factors", "item_factors")]
+        shapes = [(self.totalUsersCount, k), (self.totalItemsCount, k)]
+        if self.rank == 0:
+            mats = [np.memmap(p, np.float32, "w+", shape=sh) for p, sh in zip(self._shm_paths, shapes)]
+            self.userFactors, self.itemFactors = mats
+            self.initSharedFactorsRandom()
+            for m_ in mats:
+                m_.flush()
+        ydist.barrier(self.group)
+        if self.rank != 0:
+            self.userFactors, self.itemFactors = [np.memmap(p, np.float32, "r+", shape=sh)
+                                                  for p, sh in zip(self._shm_paths, shapes)]
+        ydist.barrier(self.group)
+        if self.rank == 0:            # every rank holds its mapping now: the names can go
+            for p in self._shm_paths:
+                os.unlink(p)
+        self.sharedHost = True
+
     def endTrain(self):
         for w in self.workers:
             w.master_side.emit("endTrain")
@@ -255,9 +282,11 @@ class EmfMaster(EmfBase):
         if stepType not in self._ranges:    # static per step: the portion plan does not change between iterations
             self._ranges[stepType] = ydist.all_ranges(self._solved_range(stepType), self.world, self.group)
         ranges = self._ranges[stepType]
+        # per-portion mode: the host segment is the truth.  With one segment shared by all ranks every rank
+        # has already written its own rows (ycnr_end_train_step); private segments need the peers' rows too.
+        private_host = not self.options["gpu"]["bulk"] and not self.sharedHost
         ydist.refresh_replicas(self.ctx, which, self.factorsCount, ranges, self.rank, self.group,
-                               host=None if self.options["gpu"]["bulk"] else
-                               (self.userFactors if which == 0 else self.itemFactors))
+                               host=(self.userFactors if which == 0 else self.itemFactors) if private_host else None)
 
     def alsTrainIter(self):
         """EmfLord.alsTrainIter (EmfLord.js:954-958)."""
