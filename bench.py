@@ -42,7 +42,10 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--fused-peers", action="store_true", help="solve kernels store rows into peer replicas")
+    ap.add_argument("--fused-peers", dest="fused_peers", action="store_true", default=True,
+                    help="N > 1: the solve kernels store rows into all peer replicas over NVLink (default)")
+    ap.add_argument("--nccl-exchange", dest="fused_peers", action="store_false",
+                    help="N > 1: refresh the replicas with an NCCL all-gather after every half-step instead")
     ap.add_argument("--gram", default="auto", choices=["auto", "ffma", "tc"])
     return ap.parse_args()
 
@@ -323,6 +326,8 @@ def main():
                          "cachePortions": True}}
         m2 = EmfMaster(table, opts2, rank=rank, world=world)
         m2.prepareToTrain()
+        if world > 1 and args.fused_peers:
+            m2.connectPeers()
         for _ in range(max(1, min(args.warmup, 2))):
             m2.trainIter()
         m2.ctx.synchronize()

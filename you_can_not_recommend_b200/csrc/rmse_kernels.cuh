@@ -137,4 +137,65 @@ __global__ void __launch_bounds__(256) rmse_portion_reduce_kernel(const double* 
   }
 }
 
+// Two-level variant for ONE big portion (the per-portion path with multi-million-rating portions): a single
+// CTA walking millions of rows is latency-bound (measured: ~5 ms for 1.7 M rows).  Level 1: one CTA per chunk
+// of kRmseChunkRows rows -> chunk_sums[c][3]; level 2: rmse_portion_reduce_chunks_kernel adds the chunks.
+// Both levels add in a fixed order, so the result does not depend on scheduling.
+constexpr int kRmseChunkRows = 4096;
+
+__global__ void __launch_bounds__(256) rmse_chunk_reduce_kernel(const double* __restrict__ row_sums,
+                                                                const int32_t* __restrict__ row_len, int n_rows,
+                                                                double* __restrict__ chunk_sums) {
+  __shared__ double s0[256], s1[256], s2[256];
+  const int lo = blockIdx.x * kRmseChunkRows, hi = min(n_rows, lo + kRmseChunkRows);
+  double d2 = 0.0, sp = 0.0, cnt = 0.0;
+  for (int r = lo + threadIdx.x; r < hi; r += 256) {
+    d2 += row_sums[2 * (size_t)r];
+    sp += row_sums[2 * (size_t)r + 1];
+    cnt += (double)row_len[r];
+  }
+  s0[threadIdx.x] = d2; s1[threadIdx.x] = sp; s2[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s0[threadIdx.x] += s0[threadIdx.x + o];
+      s1[threadIdx.x] += s1[threadIdx.x + o];
+      s2[threadIdx.x] += s2[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    chunk_sums[3 * (size_t)blockIdx.x] = s0[0];
+    chunk_sums[3 * (size_t)blockIdx.x + 1] = s2[0];
+    chunk_sums[3 * (size_t)blockIdx.x + 2] = s1[0];
+  }
+}
+
+__global__ void __launch_bounds__(256) rmse_portion_reduce_chunks_kernel(const double* __restrict__ chunk_sums,
+                                                                         int n_chunks,
+                                                                         double* __restrict__ portion_sums) {
+  __shared__ double s[3][256];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (int c = threadIdx.x; c < n_chunks; c += 256) {
+    a0 += chunk_sums[3 * (size_t)c];
+    a1 += chunk_sums[3 * (size_t)c + 1];
+    a2 += chunk_sums[3 * (size_t)c + 2];
+  }
+  s[0][threadIdx.x] = a0; s[1][threadIdx.x] = a1; s[2][threadIdx.x] = a2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s[0][threadIdx.x] += s[0][threadIdx.x + o];
+      s[1][threadIdx.x] += s[1][threadIdx.x + o];
+      s[2][threadIdx.x] += s[2][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    portion_sums[0] = s[0][0];   // rSumDiff2
+    portion_sums[1] = s[1][0];   // rCnt
+    portion_sums[2] = s[2][0];   // rSum
+  }
+}
+
 }  // namespace ycnr

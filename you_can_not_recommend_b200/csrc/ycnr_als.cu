@@ -496,7 +496,7 @@ int run_als(ycnr_ctx* c, int step_type, const RowsView& view, const DevPlan& p, 
 }
 
 int run_rmse(ycnr_ctx* c, const RowsView& view, int n_rows, int64_t nnz, double shift, double* d_row_sums,
-             const int32_t* d_portion_first, int n_portions, double* d_portion_sums) {
+             const int32_t* d_portion_first, int n_portions, double* d_portion_sums, double* d_chunk_sums = nullptr) {
   if (n_rows <= 0 || n_portions <= 0) return 0;
   ycnr::RmseArgs a{};
   a.rows = view;
@@ -511,7 +511,15 @@ int run_rmse(ycnr_ctx* c, const RowsView& view, int n_rows, int64_t nnz, double 
     const int warps_per_cta = 8;
     ycnr::rmse_rows_kernel<<<(n_rows + warps_per_cta - 1) / warps_per_cta, 256, 0, c->stream>>>(a);
   }
-  {
+  if (d_chunk_sums && n_portions == 1 && n_rows > 2 * ycnr::kRmseChunkRows) {
+    // one big portion (per-portion path): two-level fixed-order reduction instead of a single CTA
+    const int nch = (n_rows + ycnr::kRmseChunkRows - 1) / ycnr::kRmseChunkRows;
+    ProfScope ps(c, YCNR_K_RMSE_REDUCE, n_portions, 0);
+    ycnr::rmse_chunk_reduce_kernel<<<nch, 256, 0, c->stream>>>(d_row_sums, view.row_len, n_rows, d_chunk_sums);
+    ycnr::rmse_portion_reduce_chunks_kernel<<<1, 256, 0, c->stream>>>(d_chunk_sums, nch, d_portion_sums);
+    c->prof.launches[YCNR_K_RMSE_REDUCE] += 1;
+    c->prof.total_launches += 1;
+  } else {
     ProfScope ps(c, YCNR_K_RMSE_REDUCE, n_portions, 0);
     ycnr::rmse_portion_reduce_kernel<<<n_portions, 256, 0, c->stream>>>(d_row_sums, view.row_len, d_portion_first,
                                                                          d_portion_sums);
@@ -683,7 +691,8 @@ int stage_rmse_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, co
   size_t o_indx = al(o_bs + (size_t)(nb + 1) * 8);
   size_t o_vals = al(o_indx + (size_t)off * 4);
   size_t o_sums = al(o_vals + (size_t)off * 4);
-  size_t dev_total = al(o_sums + (size_t)(2 * R + 3) * 8);
+  // sums: row_sums[R][2] | portion_sums[3] | chunk_sums[ceil(R / chunk)][3]
+  size_t dev_total = al(o_sums + ((size_t)(2 * R + 3) + 3 * ((size_t)R / ycnr::kRmseChunkRows + 2)) * 8);
 
   Slot& sl = c->slots[c->next_slot];
   c->next_slot = (c->next_slot + 1) % kSlots;
@@ -1077,7 +1086,7 @@ int ycnr_rmse_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, con
   double sums[3] = {0, 0, 0};
   if (s.n_rows > 0) {
     double* d_portion = s.d_sums + 2 * (size_t)s.n_rows;
-    OK(run_rmse(c, s.view, s.n_rows, s.ratings, c->rmse_shift, s.d_sums, s.d_pfirst, 1, d_portion));
+    OK(run_rmse(c, s.view, s.n_rows, s.ratings, c->rmse_shift, s.d_sums, s.d_pfirst, 1, d_portion, d_portion + 3));
     CU(cudaMemcpyAsync(sums, d_portion, sizeof(sums), cudaMemcpyDeviceToHost, c->stream));
   }
   OK(finish_slot(c, s.slot));

@@ -275,7 +275,7 @@ class EmfMaster(EmfBase):
 
     def _refresh_replicas(self, stepType):
         which = native.USER_FACTORS if stepType == "byUser" else native.ITEM_FACTORS
-        if self.fusedPeers and self.options["gpu"]["bulk"]:
+        if self.fusedPeers and (self.options["gpu"]["bulk"] or self.sharedHost):
             self.ctx.synchronize()          # my peer stores are complete ...
             ydist.barrier(self.group)       # ... and so are everybody else's into my replica
             return
