@@ -108,7 +108,7 @@ enum {
   YCNR_K_REDUCE_SOLVE = 3,   /* sum partials + ridge + Cholesky solve */
   YCNR_K_RMSE_ROWS = 4,
   YCNR_K_RMSE_REDUCE = 5,
-  YCNR_K_GATHER = 6,
+  YCNR_K_GATHER = 6,            /* data-movement kernels: row gather, header unpack, recommend */
   YCNR_K_GRAM_TC = 7,        /* tcgen05 3xTF32 Gram */
   YCNR_K_CLASSES = 8
 };
@@ -188,6 +188,17 @@ int ycnr_ipc_close(ycnr_ctx* ctx, void* dptr);
 /* Peer replicas of matrix 'which': the solve kernels store every solved row into each of
  * them as well (fused all-gather).  n_peers = 0 clears. Max 7 peers. */
 int ycnr_set_peers(ycnr_ctx* ctx, int32_t which, int32_t n_peers, void* const* peer_dptrs);
+
+/* ---- serving: top-N recommendation ------------------------ */
+/* YcnrController.recommendItemsForUser (lib/YcnrController.js:227-284) for a batch of users, from the device
+ * replicas: every item that is not in the user's skip list (rated + "unrated" items, 244-251; 0-based ids,
+ * skip_ptr[n_users+1] indexes skip_ids) gets predict = fp32 dot(U[u], V[i]) + global_avg_shift; items with
+ * predict >= min_recommend_rating compete, best first, ties: lower item id first.  Upstream pops the last entry
+ * whenever its list reaches `limit` (281-282), so at most limit-1 items come back: out_item_ids / out_predict
+ * are [n_users][limit-1] (0-based item ids), out_count[n_users].  Synchronous. */
+int ycnr_recommend_batch(ycnr_ctx* ctx, int32_t n_users, const int32_t* user_ids, const int64_t* skip_ptr,
+                         const int32_t* skip_ids, int32_t limit, double min_recommend_rating,
+                         double global_avg_shift, int32_t* out_item_ids, double* out_predict, int32_t* out_count);
 
 /* ---- diagnostics ------------------------------------------------------------ */
 /* Copy the tile partials ([items][tiles][16] floats) left by the last split-row launch. */

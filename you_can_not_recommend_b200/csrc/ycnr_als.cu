@@ -16,6 +16,7 @@
 #include "als_kernels.cuh"
 #include "gram_tc.cuh"
 #include "portion_kernels.cuh"
+#include "recommend_kernels.cuh"
 #include "rmse_kernels.cuh"
 
 #ifndef YCNR_REDUCE_TPT
@@ -238,6 +239,11 @@ struct ycnr_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D of portion inputs, overlaps the previous portion's kernels
   cudaEvent_t copied = nullptr;
+  // per-portion path: the dual bins of a portion are small launches (about one wave each at 8 M ratings);
+  // spread over these streams they run concurrently and fill each other's tail waves
+  static constexpr int kBinStreams = 3;
+  cudaStream_t bin_stream[kBinStreams] = {nullptr};
+  cudaEvent_t fork_ev = nullptr, join_ev[kBinStreams] = {nullptr};
   cudaStream_t d2h_stream = nullptr;    // solved rows -> host factor segment, overlaps the next portion
   bool d2h_pending = false;
   cudaStream_t aux_stream = nullptr;    // reduce+solve of split rows, overlapping the next Gram chunk
@@ -426,7 +432,8 @@ constexpr int dual_nt(int mt) {
 }
 
 template <int MT_MAX, int NT>
-int launch_dual_bin(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t ratings, const int32_t* work) {
+int launch_dual_bin(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t ratings, const int32_t* work,
+                    cudaStream_t st) {
   using namespace ycnr;
   if (count <= 0) return 0;
   DualArgs a = base;
@@ -439,18 +446,19 @@ int launch_dual_bin(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t 
     CU(cudaFuncSetAttribute(als_dual_kernel<MT_MAX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  ProfScope ps(c, YCNR_K_DUAL_FUSED, count, ratings);
-  als_dual_kernel<MT_MAX, NT><<<count, NT, smem, c->stream>>>(a);
+  ProfScope ps(c, YCNR_K_DUAL_FUSED, count, ratings, st);
+  als_dual_kernel<MT_MAX, NT><<<count, NT, smem, st>>>(a);
   CU(cudaGetLastError());
   return 0;
 }
 
 template <int... B>
-int launch_dual_bins(ycnr_ctx* c, const ycnr::DualArgs& d, const DevPlan& p, const int32_t* plan_base,
+int launch_dual_bins(ycnr_ctx* c, const ycnr::DualArgs& d, const DevPlan& p, const int32_t* plan_base, bool spread,
                      std::integer_sequence<int, B...>) {
   int rc = 0;
   ((rc = rc ? rc
-            : launch_dual_bin<B + 1, dual_nt(B + 1)>(c, d, p.n_dual[B], p.ratings_dual[B], plan_base + p.off_dual[B])),
+            : launch_dual_bin<B + 1, dual_nt(B + 1)>(c, d, p.n_dual[B], p.ratings_dual[B], plan_base + p.off_dual[B],
+                                                     spread ? c->bin_stream[B % ycnr_ctx::kBinStreams] : c->stream)),
    ...);
   return rc;
 }
@@ -462,7 +470,8 @@ int dual_pitch(int k) {
 }
 
 // One ALS half-step over a device-resident row list + plan.
-int run_als(ycnr_ctx* c, int step_type, const RowsView& view, const DevPlan& p, const int32_t* plan_base) {
+int run_als(ycnr_ctx* c, int step_type, const RowsView& view, const DevPlan& p, const int32_t* plan_base,
+            bool spread = false) {
   const int solved = step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
   const int fixed = 1 - solved;
   const double lambda = step_type == YCNR_BY_USER ? c->opts.user_fact_reg : c->opts.item_fact_reg;
@@ -484,8 +493,18 @@ int run_als(ycnr_ctx* c, int step_type, const RowsView& view, const DevPlan& p, 
   // long rows first: their reduce+solve chunks run on the aux stream under the dual kernels too
   CU(cudaEventRecord(c->chunk_ev[kMaxChunks], c->stream));
   CU(cudaStreamWaitEvent(c->aux_stream, c->chunk_ev[kMaxChunks], 0));   // aux starts after everything queued so far
+  if (spread) {   // everything queued on the main stream so far (the portion's H2D wait included) precedes the bins
+    CU(cudaEventRecord(c->fork_ev, c->stream));
+    for (int i = 0; i < ycnr_ctx::kBinStreams; ++i) CU(cudaStreamWaitEvent(c->bin_stream[i], c->fork_ev, 0));
+  }
   OK(launch_primal(c, a, p, plan_base));
-  OK(launch_dual_bins(c, d, p, plan_base, std::make_integer_sequence<int, kDualBins>{}));
+  OK(launch_dual_bins(c, d, p, plan_base, spread, std::make_integer_sequence<int, kDualBins>{}));
+  if (spread) {
+    for (int i = 0; i < ycnr_ctx::kBinStreams; ++i) {
+      CU(cudaEventRecord(c->join_ev[i], c->bin_stream[i]));
+      CU(cudaStreamWaitEvent(c->stream, c->join_ev[i], 0));
+    }
+  }
   if (c->aux_pending) {
     CU(cudaEventRecord(c->chunk_ev[kMaxChunks + 1], c->aux_stream));
     CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[kMaxChunks + 1], 0));
@@ -846,6 +865,11 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   CU(cudaEventCreateWithFlags(&c->copied, cudaEventDisableTiming));
   CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+  for (int i = 0; i < ycnr_ctx::kBinStreams; ++i) {
+    CU(cudaStreamCreateWithFlags(&c->bin_stream[i], cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
+  }
   for (auto& e : c->chunk_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (int w = 0; w < 2; ++w) CU(cudaMalloc(&c->d_fac[w], (size_t)c->fac_rows[w] * c->k * sizeof(float)));
   *out = c;
@@ -879,6 +903,11 @@ int ycnr_destroy(ycnr_ctx* c) {
   for (auto e : c->chunk_ev) if (e) cudaEventDestroy(e);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+  for (int i = 0; i < ycnr_ctx::kBinStreams; ++i) {
+    if (c->bin_stream[i]) { cudaStreamSynchronize(c->bin_stream[i]); cudaStreamDestroy(c->bin_stream[i]); }
+    if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]);
+  }
+  if (c->fork_ev) cudaEventDestroy(c->fork_ev);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -997,7 +1026,7 @@ int ycnr_als_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, cons
   OK(stage_portion(c, rows, indx, vals, true, s));
   if (s.n_rows > 0) {
     const double tl0 = now_ms();
-    OK(run_als(c, c->step_type, s.view, s.plan, s.plan_base));
+    OK(run_als(c, c->step_type, s.view, s.plan, s.plan_base, true));
     c->t_launch += now_ms() - tl0;
     const int solved = c->step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
     if (c->h_fac[solved] && c->h_registered[solved]) {
@@ -1290,6 +1319,73 @@ int ycnr_set_peers(ycnr_ctx* c, int32_t which, int32_t n, void* const* ptrs) {
   OK(set_device(c));
   CU(cudaStreamSynchronize(c->stream));
   c->peers[which].assign(ptrs, ptrs + n);
+  return 0;
+}
+
+// ---- serving ----------------------------------------------------------------------------------
+int ycnr_recommend_batch(ycnr_ctx* c, int32_t n_users, const int32_t* user_ids, const int64_t* skip_ptr,
+                         const int32_t* skip_ids, int32_t limit, double min_recommend_rating,
+                         double global_avg_shift, int32_t* out_item_ids, double* out_predict, int32_t* out_count) {
+  if (!c || n_users < 0 || limit < 1 || (n_users && (!user_ids || !skip_ptr || !out_count)))
+    return fail("ycnr_recommend_batch: bad argument");
+  const int keep = limit - 1;   // YcnrController.js:281-282
+  if (keep > 0 && n_users && (!out_item_ids || !out_predict)) return fail("ycnr_recommend_batch: null output");
+  for (int u = 0; u < n_users; ++u) {
+    if (user_ids[u] < 0 || user_ids[u] >= c->fac_rows[0]) return fail("ycnr_recommend_batch: user id %d out of range", user_ids[u]);
+    if (skip_ptr[u + 1] < skip_ptr[u]) return fail("ycnr_recommend_batch: skip_ptr not monotone");
+  }
+  if (n_users && skip_ptr[n_users] > skip_ptr[0] && !skip_ids) return fail("ycnr_recommend_batch: null skip_ids");
+  if (n_users == 0) return 0;
+  if (keep == 0) { memset(out_count, 0, sizeof(int32_t) * n_users); return 0; }
+  OK(set_device(c));
+  OK(ensure_fixed_current(c, YCNR_USER_FACTORS));
+  OK(ensure_fixed_current(c, YCNR_ITEM_FACTORS));
+  const int n_items = (int)c->fac_rows[1];
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const int chunk = std::max(1, std::min(n_users, (int)(((size_t)512 << 20) / ((size_t)n_items * 8))));   // <= 512 MB of scratch
+  for (int u0 = 0; u0 < n_users; u0 += chunk) {
+    const int nu = std::min(chunk, n_users - u0);
+    const int64_t s0 = skip_ptr[u0], ns = skip_ptr[u0 + nu] - s0;
+    std::vector<int64_t> rel(nu + 1);
+    for (int u = 0; u <= nu; ++u) rel[u] = skip_ptr[u0 + u] - s0;
+    const size_t o_ptr = 0, o_uid = al(o_ptr + (size_t)(nu + 1) * 8), o_skip = al(o_uid + (size_t)nu * 4);
+    const size_t o_cnt = al(o_skip + (size_t)ns * 4), o_oid = al(o_cnt + (size_t)nu * 4);
+    const size_t o_opr = al(o_oid + (size_t)nu * keep * 4), o_pred = al(o_opr + (size_t)nu * keep * 8);
+    OK(c->gather_tmp.ensure(al(o_pred + (size_t)nu * n_items * 8)));
+    char* d = (char*)c->gather_tmp.p;
+    CU(cudaMemcpyAsync(d + o_ptr, rel.data(), (size_t)(nu + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + o_uid, user_ids + u0, (size_t)nu * 4, cudaMemcpyHostToDevice, c->stream));
+    if (ns) CU(cudaMemcpyAsync(d + o_skip, skip_ids + s0, (size_t)ns * 4, cudaMemcpyHostToDevice, c->stream));
+    ycnr::RecommendArgs a{};
+    a.U = c->d_fac[YCNR_USER_FACTORS];
+    a.V = c->d_fac[YCNR_ITEM_FACTORS];
+    a.k = c->k;
+    a.n_items = n_items;
+    a.n_users = nu;
+    a.user_ids = (const int32_t*)(d + o_uid);
+    a.skip_ptr = (const int64_t*)(d + o_ptr);
+    a.skip_ids = (const int32_t*)(d + o_skip);
+    a.shift = global_avg_shift;
+    a.min_rating = min_recommend_rating;
+    a.keep = keep;
+    a.pred = (double*)(d + o_pred);
+    a.out_ids = (int32_t*)(d + o_oid);
+    a.out_pred = (double*)(d + o_opr);
+    a.out_count = (int32_t*)(d + o_cnt);
+    {
+      ProfScope ps(c, YCNR_K_GATHER, nu, (int64_t)nu * n_items);
+      dim3 grid((n_items + ycnr::kRecItemsPerCta - 1) / ycnr::kRecItemsPerCta, nu);
+      ycnr::recommend_scores_kernel<<<grid, 256, 0, c->stream>>>(a);
+      ycnr::recommend_select_kernel<<<nu, 256, 0, c->stream>>>(a);
+      c->prof.launches[YCNR_K_GATHER] += 1;
+      c->prof.total_launches += 1;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_count + u0, d + o_cnt, (size_t)nu * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out_item_ids + (size_t)u0 * keep, d + o_oid, (size_t)nu * keep * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out_predict + (size_t)u0 * keep, d + o_opr, (size_t)nu * keep * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
   return 0;
 }
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "ycnr_stream", "ycnr_synchronize", "ycnr_host_register", "ycnr_host_unregister", "ycnr_start_train_step", "ycnr_als_portion", "ycnr_end_train_step",
     "ycnr_start_calc_rmse", "ycnr_rmse_portion", "ycnr_s_als_build_sub_fixed_facts", "ycnr_rowset_create",
     "ycnr_rowset_destroy", "ycnr_als_rowset", "ycnr_rmse_rowset", "ycnr_ipc_export", "ycnr_ipc_import",
-    "ycnr_ipc_close", "ycnr_set_peers", "ycnr_debug_read_partials", "ycnr_profile_reset", "ycnr_profile_read",
+    "ycnr_ipc_close", "ycnr_set_peers", "ycnr_recommend_batch", "ycnr_debug_read_partials", "ycnr_profile_reset", "ycnr_profile_read",
 ]
 
 
@@ -216,6 +216,27 @@ class Context:
     def set_peers(self, which, ptrs):
         arr = (C.c_void_p * max(1, len(ptrs)))(*ptrs)
         _check(lib().ycnr_set_peers(self._h, C.c_int32(which), C.c_int32(len(ptrs)), arr))
+
+    # -- serving
+    def recommend_batch(self, user_ids, skip_lists, limit=20, min_recommend_rating=0.0, global_avg_shift=0.0):
+        """Top-N for a batch of users (0-based ids). skip_lists: one iterable of 0-based item ids per user.
+        Returns a list (per user) of (item_id, predict) pairs, best first, at most limit-1 of them."""
+        user_ids = np.ascontiguousarray(user_ids, np.int32)
+        n = len(user_ids)
+        ptr = np.zeros(n + 1, np.int64)
+        for i, sl in enumerate(skip_lists):
+            ptr[i + 1] = ptr[i] + len(sl)
+        skip = np.zeros(max(1, int(ptr[-1])), np.int32)
+        for i, sl in enumerate(skip_lists):
+            skip[ptr[i]:ptr[i + 1]] = np.asarray(sl, np.int32)
+        keep = max(limit - 1, 0)
+        ids = np.zeros((n, max(keep, 1)), np.int32)
+        pred = np.zeros((n, max(keep, 1)), np.float64)
+        cnt = np.zeros(max(n, 1), np.int32)
+        _check(lib().ycnr_recommend_batch(self._h, C.c_int32(n), _i32(user_ids), _i64(ptr), _i32(skip), C.c_int32(limit),
+                                          C.c_double(min_recommend_rating), C.c_double(global_avg_shift),
+                                          _i32(ids), pred.ctypes.data_as(C.POINTER(C.c_double)), _i32(cnt)))
+        return [[(int(ids[u, j]), float(pred[u, j])) for j in range(int(cnt[u]))] for u in range(n)]
 
     def debug_read_partials(self, n_items, n_tiles):
         out = np.zeros((n_items, n_tiles, 4, 4), np.float32)
