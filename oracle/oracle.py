@@ -151,3 +151,29 @@ class OracleTrainer:
         for _ in range(iters):
             self.train_iter()
         return self.history
+
+
+def recommend_items_for_user(U, V, user_id0, skip_item_ids0, limit=20, min_recommend_rating=0.0,
+                             global_avg_shift=0.0):
+    """Literal restatement of YcnrController.recommendItemsForUser (lib/YcnrController.js:227-284), 0-based ids.
+
+    The loop is upstream's: push, sort by predict descending (a stable sort, as in current V8), raise
+    minRatingInSelection, and pop the last entry whenever the list has reached `limit` (281-282) — which is
+    why at most limit-1 items come back.  predict = fp32 dot + shift in double (EmfBase.js:815-827).
+    Returns [(item_id0, predict)], best first."""
+    skip = set(int(i) for i in skip_item_ids0)                 # skipItemIds, 244-251
+    uf = np.asarray(U[user_id0], np.float32)
+    rec = []
+    min_in_sel = 0.0
+    for item in range(V.shape[0]):                             # 264
+        if item in skip:
+            continue
+        predict = float(np.dot(uf, np.asarray(V[item], np.float32))) + global_avg_shift
+        if predict >= min_recommend_rating and (len(rec) < limit or predict > min_in_sel):   # 271-272
+            rec.append((item, predict))
+            rec.sort(key=lambda t: -t[1])                      # 274 (list.sort is stable)
+            if predict > min_in_sel:
+                min_in_sel = predict                           # 275-276
+            if len(rec) >= limit:
+                rec.pop()                                      # 277-278
+    return rec

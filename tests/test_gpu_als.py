@@ -364,3 +364,49 @@ def test_full_size_mal_properties():
     assert tot[1] == int(m.rowlists["rmseValidate"][1].sum(dtype=np.int64))
     assert np.isfinite(tot[0]) and tot[0] > 0
     m.endTrain()
+
+
+@pytest.mark.parametrize("k,limit", [(20, 20), (100, 5), (7, 1)])
+def test_recommend_batch_vs_oracle(k, limit):
+    """Top-N serving (YcnrController.js:227-284): same items in the same order as the literal restatement of
+    the controller loop, predictions within fp32 summation-order noise (1e-5 relative), including the
+    upstream quirk that at most limit-1 items come back, the skip list and the threshold."""
+    users, items = 50, 700
+    rng = np.random.default_rng(5)
+    U = rng.normal(0.6, 0.3, (users, k)).astype(np.float32)
+    V = rng.normal(0.6, 0.3, (items, k)).astype(np.float32)
+    ctx = native.Context(k, users, items)
+    ctx.attach_factors(U, V)
+    uids = [0, 7, 49, 7]
+    skips = [rng.choice(items, n, replace=False).astype(np.int32) for n in (0, 150, 699, 3)]
+    shift = 0.123
+    thr = float(np.median(U[7] @ V.T)) + shift          # a threshold that cuts about half of the items
+    for min_rating in (-1e30, thr):
+        got = ctx.recommend_batch(uids, skips, limit, min_rating, shift)
+        for u, sk, rec in zip(uids, skips, got):
+            want = oracle.recommend_items_for_user(U, V, u, sk, limit, min_rating, shift)
+            assert len(rec) == len(want) <= max(limit - 1, 0)
+            assert [i for i, _ in rec] == [i for i, _ in want]
+            for (_, p), (_, q) in zip(rec, want):
+                assert abs(p - q) <= 1e-5 * max(1.0, abs(q))
+            assert not set(i for i, _ in rec) & set(sk.tolist())
+    ctx.close()
+
+
+def test_recommend_through_master_mirror():
+    """recommendItemsForUser on the host mirror: 1-based ids, rated items skipped, after one ALS iteration."""
+    prob = make_problem("ml-100k", k=20)
+    m = EmfMaster(prob["table"], {"factorsCount": 20, "seed": prob["seed"], "gpu": {"bulk": True}})
+    m.prepareToTrain(prob["U0"].copy(), prob["V0"].copy())
+    m.trainIter()
+    m.syncFactorsToHost()
+    user = {"list_id": 5, "unrated_items": [1, 2, 3]}
+    rec = m.recommendItemsForUser(user, limit=10, minRecommendRating=1.0)
+    t = prob["table"]
+    rated = set((t.item_ids[t.user_ptr[4]:t.user_ptr[5]] + 1).tolist()) | {1, 2, 3}
+    want = oracle.recommend_items_for_user(m.userFactors, m.itemFactors, 4, [i - 1 for i in rated], 10, 1.0,
+                                           m.globalAvgShift)
+    assert 0 < len(rec) <= 9 and [r["id"] for r in rec] == [i + 1 for i, _ in want]
+    assert all(r["id"] not in rated and r["predict"] >= 1.0 for r in rec)
+    assert all(a["predict"] >= b["predict"] for a, b in zip(rec, rec[1:]))
+    m.endTrain()

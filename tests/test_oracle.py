@@ -103,3 +103,18 @@ def test_q7_shift_uses_last_portion_only():
     rows, indx, vals = portions["rmseTest"][-1]
     _, cnt, s = oracle.rmse_portion(rows, indx, vals, tr.U, tr.V, 0.0)
     assert tr.global_avg_shift == 3.0 - s / cnt
+
+
+def test_recommend_restatement_quirks():
+    """YcnrController.recommendItemsForUser (lib/YcnrController.js:227-284) by hand: k = 1, user factor 1, so
+    predict = item factor + shift.  At most limit-1 items come back (the pop at 281-282), best first, skip list
+    and threshold respected, ties keep the lower item id."""
+    U = np.asarray([[1.0]], np.float32)
+    V = np.asarray([[3.0], [5.0], [1.0], [5.0], [4.0], [2.0]], np.float32)
+    rec = oracle.recommend_items_for_user(U, V, 0, [], limit=4, min_recommend_rating=0.0, global_avg_shift=0.5)
+    assert rec == [(1, 5.5), (3, 5.5), (4, 4.5)]                      # 3 = limit - 1 entries
+    rec = oracle.recommend_items_for_user(U, V, 0, [1], limit=4, min_recommend_rating=2.6, global_avg_shift=0.5)
+    assert rec == [(3, 5.5), (4, 4.5), (0, 3.5)]
+    rec = oracle.recommend_items_for_user(U, V, 0, [1, 3], limit=10, min_recommend_rating=3.6, global_avg_shift=0.5)
+    assert rec == [(4, 4.5)]
+    assert oracle.recommend_items_for_user(U, V, 0, [], limit=1) == []

@@ -380,6 +380,26 @@ class EmfMaster(EmfBase):
             self.syncFactorsToHost()
         return self.history
 
+    # ---- serving (YcnrController.recommendItemsForUser, lib/YcnrController.js:227-284) -----------------
+    def recommendItemsForUsers(self, users, limit=20, minRecommendRating=0.0):
+        """Batched form of the controller's brute-force top-N.  users: dicts {'list_id': 1-based id,
+        'unrated_items': [1-based item ids]} as upstream; the rated items come from the ratings table
+        (the SQL at 233-239).  Returns per user a list of {'predict', 'id' (1-based)}, best first —
+        at most limit-1 entries, like upstream (281-282)."""
+        t = self.table
+        uids, skips = [], []
+        for u in users:
+            u0 = int(u["list_id"]) - 1
+            rated = t.item_ids[t.user_ptr[u0]:t.user_ptr[u0 + 1]]
+            unrated = np.asarray(u.get("unrated_items") or [], np.int32) - 1
+            uids.append(u0)
+            skips.append(np.concatenate([rated, unrated]).astype(np.int32))
+        out = self.ctx.recommend_batch(uids, skips, limit, minRecommendRating, self.globalAvgShift)
+        return [[{"predict": p, "id": i + 1} for i, p in rec] for rec in out]
+
+    def recommendItemsForUser(self, user, limit=20, minRecommendRating=0.0):
+        return self.recommendItemsForUsers([user], limit, minRecommendRating)[0]
+
     def syncFactorsToHost(self):
         """Bulk mode keeps the factors on the device; copy both matrices into the host segments."""
         self.ctx.download_factors(native.USER_FACTORS)

@@ -208,6 +208,54 @@ napi_value DAlsBuildSubFixedFacts(napi_env env, napi_callback_info) {
   return nullptr;
 }
 
+// hostRegister(handle, typedArray): page-lock a portion-cache buffer (usePortionsCache) for direct DMA
+napi_value HostRegister(napi_env env, napi_callback_info info) {
+  napi_value a[2];
+  ycnr_ctx* c;
+  if (!args(env, info, 2, a) || !handle(env, a[0], &c)) return nullptr;
+  napi_typedarray_type t;
+  size_t len = 0;
+  void* p = nullptr;
+  if (napi_get_typedarray_info(env, a[1], &t, &len, &p, nullptr, nullptr) != napi_ok || !p) {
+    fail(env, "invalid type!");
+    return nullptr;
+  }
+  const size_t elem = (t == napi_float64_array) ? 8 : (t == napi_int8_array || t == napi_uint8_array || t == napi_uint8_clamped_array) ? 1
+                      : (t == napi_int16_array || t == napi_uint16_array) ? 2 : 4;
+  check(env, ycnr_host_register(c, p, len * elem));
+  return undefined(env);
+}
+
+// recommend(handle, Int32Array userIds, Float64Array skipPtr /*[n+1] offsets*/, Int32Array skipIds, limit,
+//           minRecommendRating, globalAvgShift, Int32Array outIds /*[n*(limit-1)]*/, Float64Array outPredict,
+//           Int32Array outCount /*[n]*/)      — YcnrController.recommendItemsForUser (YcnrController.js:227-284), 0-based ids
+napi_value Recommend(napi_env env, napi_callback_info info) {
+  napi_value a[10];
+  ycnr_ctx* c;
+  int32_t *uids, *skip, *oids, *ocnt, limit;
+  double *sptr, *opred, min_rating, shift;
+  size_t nu, nsp, ns, noi, nop, noc;
+  if (!args(env, info, 10, a) || !handle(env, a[0], &c) || !typed(env, a[1], napi_int32_array, &uids, &nu) ||
+      !typed(env, a[2], napi_float64_array, &sptr, &nsp) || !typed(env, a[3], napi_int32_array, &skip, &ns) ||
+      napi_get_value_int32(env, a[4], &limit) != napi_ok || napi_get_value_double(env, a[5], &min_rating) != napi_ok ||
+      napi_get_value_double(env, a[6], &shift) != napi_ok || !typed(env, a[7], napi_int32_array, &oids, &noi) ||
+      !typed(env, a[8], napi_float64_array, &opred, &nop) || !typed(env, a[9], napi_int32_array, &ocnt, &noc))
+    return nullptr;
+  if (limit < 1 || nsp != nu + 1 || noc < nu || noi < nu * (size_t)(limit - 1) || nop < nu * (size_t)(limit - 1)) {
+    fail(env, "recommend: array sizes do not match");
+    return nullptr;
+  }
+  int64_t* ptr = new int64_t[nu + 1];   // JS has no Int64Array before BigInt: offsets travel as doubles
+  for (size_t i = 0; i <= nu; ++i) ptr[i] = (int64_t)sptr[i];
+  const int rc = (ptr[nu] < 0 || (size_t)ptr[nu] > ns)
+                     ? -1
+                     : ycnr_recommend_batch(c, (int32_t)nu, uids, ptr, skip, limit, min_rating, shift, oids, opred, ocnt);
+  delete[] ptr;
+  if (rc == -1) fail(env, "recommend: skipPtr exceeds skipIds");
+  else check(env, rc);
+  return undefined(env);
+}
+
 napi_value Destroy(napi_env env, napi_callback_info info) {
   // contexts are released by the external's finalizer; explicit destroy only synchronises
   napi_value a[1];
@@ -228,6 +276,8 @@ napi_value Init(napi_env env, napi_value exports) {
       {"rmsePortion", nullptr, RmsePortion, nullptr, nullptr, nullptr, 0, nullptr},
       {"sAlsBuildSubFixedFacts", nullptr, SAlsBuildSubFixedFacts, nullptr, nullptr, nullptr, 0, nullptr},
       {"dAlsBuildSubFixedFacts", nullptr, DAlsBuildSubFixedFacts, nullptr, nullptr, nullptr, 0, nullptr},
+      {"hostRegister", nullptr, HostRegister, nullptr, nullptr, nullptr, 0, nullptr},
+      {"recommend", nullptr, Recommend, nullptr, nullptr, nullptr, 0, nullptr},
       {"destroy", nullptr, Destroy, nullptr, nullptr, nullptr, 0, nullptr},
   };
   napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
