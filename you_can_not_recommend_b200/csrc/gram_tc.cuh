@@ -30,15 +30,31 @@
 // masked operands), so only the tail l = y - tf32(y) has to be produced by CUDA cores:
 // one LDS, one STS and 8 ALU ops per 16 bytes.
 //
-// CTA = 1 per SM (all 512 TMEM columns: two 256-column accumulators), warp-specialised:
+// CTA = 1 per SM (all 512 TMEM columns: two 256-column accumulators), warp-specialised (29 warps at k = 100):
 //   warps 0-3    epilogue: tcgen05.ld -> smem X -> symmetrise -> tile partials to HBM
 //   warp  4      TMEM alloc + single-thread MMA issue (tcgen05.mma / tcgen05.commit)
-//   next STAGES warps  loaders: warp w owns ring slot w; one cp.async instruction moves one rating
-//                (lane = 16-byte chunk), column ids are broadcast by shuffle.  Completion is
-//                signalled per stage with cp.async.mbarrier.arrive; loaders never execute a
-//                fence, so up to STAGES stages of copies stay in flight against HBM latency
-//   next STAGES warps  splitters: warp w owns ring slot w: tail columns, fence.proxy.async, hand
-//                the stage to the MMA warp
+//   next 2*STAGES warps  loaders: two per ring slot, each moving one half (16 ratings) of every stage of
+//                its slot; one cp.async instruction moves one rating (lane = 16-byte chunk), column ids are
+//                broadcast by shuffle.  Completion is signalled per stage with cp.async.mbarrier.arrive;
+//                loaders never execute a fence, so up to STAGES stages of copies stay in flight.  When the
+//                fixed matrix does not fit L2 (byItem gathers from U), each loader also issues
+//                prefetch.global.L2 for the rows it will gather two ring cycles later, so the bytes in flight
+//                against HBM latency are not capped by the ring's shared memory
+//   next 2*STAGES warps  splitters: two per ring slot: tail columns (four LDS.128 in flight),
+//                fence.proxy.async, hand the stage to the MMA warp
+// A warp always works on the same slot: seeing every use of "its" slot in order is what makes waiting on an
+// mbarrier phase PARITY sound.
+//
+// Measured history (B200, MAL k = 100, byUser 69 M + byItem 116 M ratings per iteration):
+//   v1  LDG -> registers -> STS producers, one warp per slot ........................ 32.0 ms
+//   v2  cp.async into the swizzled layout, 1 loader + 1 splitter warp per slot ....... 27.1 ms
+//       same, 12 stages of 16 ratings ............................................... 28.2 ms
+//   v3  register-staged producers, 2 warps per slot .................................. 29.8 ms
+//   v4  (this file) 2 loaders + 2 splitters per slot, 4-deep LDS, L2 prefetch ........ 21.7 ms
+//   v5  register-staged producers, 4 warps per slot + L2 prefetch (ld.global.cg) ..... 25.1 ms
+// ncu source view of v2: a slot's cycle was loader issue 1.8k clk -> arrival -> splitter 3k clk (LDS latency
+// exposed) -> MMA; loaders spent 77 % and the epilogue 97 % of their samples waiting, i.e. the ring was bound
+// by the two producer legs, which v4 halves.  v4: tensor pipe 42-50 % active, LSU data pipe 64 %.
 #pragma once
 #include "als_kernels.cuh"
 #include "common.cuh"
