@@ -215,6 +215,8 @@ struct PrimalArgs {
   // slices of long rows
   const int32_t* __restrict__ item_row;   // MODE_PARTIAL: row index per work item
   const int32_t* __restrict__ item_off;   // MODE_PARTIAL: first rating of the slice inside the row
+  const int32_t* __restrict__ item_order; // tensor-core Gram: processing order of the work items (longest first)
+  int n_items_total;
   int split_cols;                         // slice length
   float* __restrict__ partial;            // [items][tiles][16]
   const int32_t* __restrict__ row_first_item;  // MODE_REDUCE: per work entry

@@ -99,6 +99,7 @@ struct GramTcArgs {
   int k;
   const int32_t* __restrict__ item_row;
   const int32_t* __restrict__ item_off;
+  const int32_t* __restrict__ item_order;   // j-th work item to process (longest slices first), or nullptr = identity
   int n_items;
   int split_cols;
   float* __restrict__ partial;   // [items][tiles][16]
@@ -142,8 +143,10 @@ __device__ __forceinline__ uint32_t tc_chunk_offset(int r, int c) {
          (uint32_t)(((((c & 31) >> 3) ^ (r & 3)) << 5) | (((c >> 2) & 1) << 4));
 }
 
-// Walks the CTA's work items stage by stage (items blockIdx.x, +gridDim.x, ...; the host never
-// emits an empty slice).  Every thread of a role walks it redundantly: the descriptor loads are
+// Walks the CTA's work items stage by stage (positions blockIdx.x, +gridDim.x, ... of item_order; the
+// host never emits an empty slice).  item_order lists the slices longest first, so this static round-robin
+// hands every CTA one slice of each length band: the CTAs' totals differ by at most one slice (~0.5 %)
+// instead of the ~7-11 % spread of the natural order.  Every thread of a role walks it redundantly: the descriptor loads are
 // warp-uniform and cache-resident, and the descriptor of the following item is requested one
 // item early so its latency is off the critical path.
 struct TcItemIter {
@@ -155,8 +158,9 @@ struct TcItemIter {
     beg = 0;
     len = 0;
     if (item < a.n_items) {
-      const int row = __ldg(a.item_row + item);
-      const int off = __ldg(a.item_off + item);
+      const int it0 = a.item_order ? __ldg(a.item_order + item) : item;
+      const int row = __ldg(a.item_row + it0);
+      const int off = __ldg(a.item_off + it0);
       beg = __ldg(a.rows.row_start + row) + off;
       len = max(0, min(a.split_cols, __ldg(a.rows.row_len + row) - off));
     }
@@ -380,43 +384,80 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
     }
   } else if (warp == 4) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
-      TcItemIter ix;
-      ix.init(a);
-      uint32_t gs = 0, itc = 0;
-      while (ix.valid(a)) {
-        const int nst = ix.nst, seg_len = ix.seg_len;
-        const uint32_t buf = itc & 1u, aph = (itc >> 1) & 1u;
-        ++itc;
-        mbar_wait(acce0 + 8 * buf, aph ^ 1u);       // epilogue drained this accumulator
+    // The whole warp walks the loop convergently and one elected lane issues (elect.sync inside the asm
+    // block, as CUTLASS's SM100 atoms do).  An earlier version ran the loop under `if (lane == 0)`: in a
+    // divergent region the compiler cannot keep the descriptors in uniform registers and wrapped every
+    // tcgen05.mma / commit in an ELECT + R2UR + BRA.U.ANY loop — ~130 dependent scalar instructions
+    // (~800 clk) per stage; ncu's source view showed this thread busy 75 % of the time and waiting on `full`
+    // only 4 %: the issue loop, not the producers or the tensor pipe, bounded the kernel.
+    // The issue loop is a serial chain of dependent scalar instructions (~5 clk each) next to a tensor pipe
+    // that needs 4 x ~114 clk per stage, so it is kept short: ring position and phase are counters (no
+    // divisions), the descriptor is one constant high word plus a low word that advances by a constant per
+    // stage / per K-group, and a full stage (the common case) is ONE asm block: elect, 4 MMAs, commit.
+    TcItemIter ix;
+    ix.init(a);
+    uint32_t itc = 0;
+    uint32_t s = 0, ph = 0;                                   // ring slot and its phase
+    const uint64_t desc0 = tc_smem_desc(smem_u32(stage_base), kTcPanelBytes, 512u, 1u);
+    const uint32_t desc_hi = (uint32_t)(desc0 >> 32);
+    const uint32_t desc_lo0 = (uint32_t)desc0;                // + (byte offset >> 4): never carries out of the address field
+    constexpr uint32_t kStageLo = Cfg::STAGE_BYTES >> 4, kGroupLo = 1024u >> 4;
+    static_assert(kTcStageRows == 32, "the full-stage block below issues exactly 4 MMAs");
+    while (ix.valid(a)) {
+      const int nst = ix.nst, seg_len = ix.seg_len;
+      const uint32_t buf = itc & 1u, aph = (itc >> 1) & 1u;
+      ++itc;
+      mbar_wait(acce0 + 8 * buf, aph ^ 1u);       // epilogue drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t d_tmem = tmem_base + buf * 256u;
+      const int nfull = seg_len / kTcStageRows;   // full stages first, then at most one short stage
+      for (int st = 0; st < nst; ++st) {
+        mbar_wait(full0 + 8 * s, ph);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t d_tmem = tmem_base + buf * 256u;
-        for (int st = 0; st < nst; ++st, ++gs) {
-          const uint32_t s = gs % STAGES, ph = (gs / STAGES) & 1u;
-          mbar_wait(full0 + 8 * s, ph);
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const int rows_here = min(kTcStageRows, seg_len - st * kTcStageRows);
+        const uint32_t lo = desc_lo0 + s * kStageLo;
+        const uint32_t bar = empty0 + 8 * s;
+        if (st < nfull) {
+          asm volatile(
+              "{\n .reg .pred p, q, t;\n .reg .b32 l1, l2, l3;\n .reg .b64 d0, d1, d2, d3;\n"
+              " setp.ne.b32 p, %4, 0;\n setp.eq.b32 t, 0, 0;\n"
+              " add.u32 l1, %1, %5;\n add.u32 l2, l1, %5;\n add.u32 l3, l2, %5;\n"
+              " mov.b64 d0, {%1, %2};\n mov.b64 d1, {l1, %2};\n mov.b64 d2, {l2, %2};\n mov.b64 d3, {l3, %2};\n"
+              " elect.sync _|q, 0xffffffff;\n"
+              " @q tcgen05.mma.cta_group::1.kind::tf32 [%0], d0, d0, %3, p;\n"
+              " @q tcgen05.mma.cta_group::1.kind::tf32 [%0], d1, d1, %3, t;\n"
+              " @q tcgen05.mma.cta_group::1.kind::tf32 [%0], d2, d2, %3, t;\n"
+              " @q tcgen05.mma.cta_group::1.kind::tf32 [%0], d3, d3, %3, t;\n"
+              " @q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n}\n" ::"r"(d_tmem),
+              "r"(lo), "r"(desc_hi), "r"(IDESC), "r"(st > 0 ? 1u : 0u), "n"(kGroupLo), "r"(bar)
+              : "memory");
+        } else {
+          const int rows_here = seg_len - st * kTcStageRows;
           const int ng = (rows_here + 7) >> 3;
-          const uint32_t sa = smem_u32(stage_base + s * Cfg::STAGE_BYTES);
           for (int g = 0; g < ng; ++g) {
-            const uint64_t desc = tc_smem_desc(sa + (uint32_t)g * 1024u, kTcPanelBytes, 512u, 1u);
             const uint32_t acc = (st > 0 || g > 0) ? 1u : 0u;
             asm volatile(
-                "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-                " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-                "l"(desc), "l"(desc), "r"(IDESC), "r"(acc)
+                "{\n .reg .pred p, q;\n .reg .b64 d;\n setp.ne.b32 p, %4, 0;\n mov.b64 d, {%1, %2};\n"
+                " elect.sync _|q, 0xffffffff;\n"
+                " @q tcgen05.mma.cta_group::1.kind::tf32 [%0], d, d, %3, p;\n}\n" ::"r"(d_tmem),
+                "r"(lo + (uint32_t)g * kGroupLo), "r"(desc_hi), "r"(IDESC), "r"(acc)
                 : "memory");
           }
           // frees the stage for the producers once the MMAs above have read it
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
-                           empty0 + 8 * s)
-                       : "memory");
+          asm volatile(
+              "{\n .reg .pred q;\n elect.sync _|q, 0xffffffff;\n"
+              " @q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar)
+              : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
-                         accf0 + 8 * buf)
-                     : "memory");
-        ix.next_item(a);
+        if (++s == (uint32_t)STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
+      asm volatile(
+          "{\n .reg .pred q;\n elect.sync _|q, 0xffffffff;\n"
+          " @q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(accf0 + 8 * buf)
+          : "memory");
+      ix.next_item(a);
     }
     __syncwarp();
   } else {
@@ -460,7 +501,8 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       mbar_arrive(acce0 + 8 * buf);
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      float* out = a.partial + (size_t)it * NTILES * 16;
+      const int it0 = a.item_order ? __ldg(a.item_order + it) : it;   // partials stay indexed by the item itself
+      float* out = a.partial + (size_t)it0 * NTILES * 16;
 #pragma unroll
       for (int j = 0; j < EPI_TPT; ++j) {
         const int t = tid + j * kTcEpiThreads;

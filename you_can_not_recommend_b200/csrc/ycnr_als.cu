@@ -87,6 +87,7 @@ struct DevPlan {
   size_t off_dual[kDualBins] = {0};
   int n_fused = 0, n_multi = 0, n_items = 0;
   size_t off_fused = 0, off_multi = 0, off_multi_first = 0, off_multi_n = 0, off_item_row = 0, off_item_off = 0;
+  size_t off_item_order = 0;
   int64_t ratings_dual[kDualBins] = {0};
   int64_t ratings_fused = 0, ratings_multi = 0;
   size_t words = 0;
@@ -130,6 +131,7 @@ void plan_count(const int32_t* len, int stride, int n_rows, const PlanCfg& cfg, 
   p.off_multi_n = o;      o += p.n_multi;
   p.off_item_row = o;     o += p.n_items;
   p.off_item_off = o;     o += p.n_items;
+  p.off_item_order = o;   o += p.n_items;
   p.words = o;
 }
 
@@ -169,6 +171,21 @@ void plan_fill(const int32_t* len, int stride, int n_rows, const PlanCfg& cfg, D
       const int lx = len[(size_t)x * stride], ly = len[(size_t)y * stride];
       return lx != ly ? lx > ly : x < y;
     });
+  }
+  // processing order of the work items for the persistent Gram kernel: longest slices first (stable counting
+  // sort on length / 32), see TcItemIter
+  {
+    int32_t* order = out + p.off_item_order;
+    const int nb = cfg.split_cols / 32 + 2;
+    std::vector<int32_t> cnt(nb + 1, 0);
+    auto bucket = [&](int i) {
+      const int n = len[(size_t)irow[i] * stride];
+      const int l = std::min(cfg.split_cols, n - ioff[i]);
+      return nb - 1 - std::min(nb - 1, l / 32);        // descending
+    };
+    for (int i = 0; i < p.n_items; ++i) cnt[bucket(i) + 1]++;
+    for (int b = 0; b < nb; ++b) cnt[b + 1] += cnt[b];
+    for (int i = 0; i < p.n_items; ++i) order[cnt[bucket(i)]++] = i;
   }
   // chunk cuts at equal cumulative ratings
   const int nm = p.n_multi;
@@ -334,6 +351,7 @@ int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int item_from, int n
     constexpr int NTILES = KT * (KT + 1) / 2 + KT;
     t.item_row = pa.item_row + item_from;
     t.item_off = pa.item_off + item_from;
+    t.item_order = (item_from == 0 && n_items == pa.n_items_total) ? pa.item_order : nullptr;   // chunked launches: natural order
     t.n_items = n_items;
     t.split_cols = pa.split_cols;
     t.partial = pa.partial + (size_t)item_from * NTILES * 16;
@@ -368,6 +386,8 @@ int launch_primal_kt(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p
     PrimalArgs a = base;
     a.item_row = plan_base + p.off_item_row;
     a.item_off = plan_base + p.off_item_off;
+    a.item_order = plan_base + p.off_item_order;
+    a.n_items_total = p.n_items;
     a.partial = (float*)c->partial.p;
     a.work = plan_base + p.off_multi;
     a.row_first_item = plan_base + p.off_multi_first;
