@@ -180,6 +180,29 @@ int ycnr_als_rowset(ycnr_ctx* ctx, int32_t rowset);
 int ycnr_rmse_rowset(ycnr_ctx* ctx, int32_t rowset, double global_avg_shift, double* totals,
                      double* portion_sums);
 
+/* ---- device-side front end --------------------------------- */
+/* The ratings table malrec_ratings (data/db-schema.sql:887-893) sorted by (user, item) as flat arrays:
+ * user_ptr[total_users+1], then per rating the 0-based item id, the rating and its dataset_type
+ * (EmfBase.js:229-247).  Uploaded once; the calls below replace the per-portion SQL fetch and the per-rating
+ * conversion loop of the master (EmfMaster.js:501-614) for whole steps. */
+int ycnr_table_upload(ycnr_ctx* ctx, const int64_t* user_ptr, const int32_t* item_ids, const float* ratings,
+                      const int8_t* dataset_type);
+/* Ratings per user (by_item = 0) or per item (by_item = 1) whose dataset_type bit is set in set_mask —
+ * the planner's ratings_count (EmfLord.js:48-128, 255-397).  counts_out[total_users | total_items]. */
+int ycnr_table_counts(ycnr_ctx* ctx, uint32_t set_mask, int32_t by_item, int32_t* counts_out);
+/* All portions of a step as a device-resident row set, built on the device: the fetch (ratings of the set
+ * grouped by user in item order, or by item in user order), then the concatenated portion headers for the
+ * plan portions_row_id_to[n_portions] (exclusive 0-based upper row bounds, EmfLord.js:510-612) with the
+ * conversion loop's quirk (the last rating of every portion is dropped, EmfMaster.js:582-609).  Same result,
+ * bit for bit, as ycnr_rowset_create on the host front end's arrays. */
+int ycnr_rowset_from_table(ycnr_ctx* ctx, int32_t step_type, uint32_t set_mask, const int32_t* portions_row_id_to,
+                           int32_t n_portions, int32_t* rowset_out);
+int ycnr_rowset_info(ycnr_ctx* ctx, int32_t rowset, int32_t* n_rows, int64_t* span, int32_t* n_portions);
+/* Copy a row set's arrays back (any pointer may be NULL): row_ids/row_start/row_len[n_rows],
+ * portion_first[n_portions+1], indx/vals[span]. */
+int ycnr_rowset_read(ycnr_ctx* ctx, int32_t rowset, int32_t* row_ids, int64_t* row_start, int32_t* row_len,
+                     int32_t* portion_first, int32_t* indx, float* vals);
+
 /* ---- multi-GPU replica refresh over NVLink peer memory --------------------- */
 /* 64-byte CUDA IPC handle of a device replica; import returns a peer-mapped pointer. */
 int ycnr_ipc_export(ycnr_ctx* ctx, int32_t which, uint8_t handle_out[64]);

@@ -142,3 +142,37 @@ def test_build_portion_overflow_is_an_error():
     csr = t.csr_by_user(fe.MASK_TRAIN)
     with pytest.raises(RuntimeError, match="exceed buffer"):
         fe.build_portion(csr, 0, t.users, t.users, 10)
+
+
+def test_q2_closed_form_equals_conversion_loop():
+    """The device ingest (csrc/ingest_kernels.cuh) does not replay the master's per-rating loop
+    (EmfMaster.js:582-609); it uses its closed form: inside every portion all non-empty rows are emitted with
+    their full count except the LAST non-empty one, which is emitted one short — and not at all when that
+    made it empty, unless it is the portion's only row.  Checked against the loop restatement on random plans."""
+    import numpy as np
+    from you_can_not_recommend_b200 import front_end as fe
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        rows = int(rng.integers(1, 30))
+        cnt = rng.integers(0, 4, rows)
+        ptr = np.zeros(rows + 1, np.int64)
+        np.cumsum(cnt, out=ptr[1:])
+        cuts = np.unique(np.concatenate([rng.integers(1, rows + 1, int(rng.integers(1, 6))), [rows]])).astype(np.int32)
+        csr = fe.Csr(ptr, np.zeros(int(ptr[-1]), np.int32), np.zeros(int(ptr[-1]), np.float32))
+        rl = fe.build_rowlist(csr, cuts)
+        ids, lens, pf = [], [], [0]
+        for p in range(len(cuts)):
+            lo, hi = (0 if p == 0 else int(cuts[p - 1])), int(cuts[p])
+            ne = [r for r in range(lo, hi) if cnt[r] > 0]
+            for r in ne:
+                if r == ne[-1]:
+                    if cnt[r] == 1 and len(ne) > 1:
+                        continue
+                    ids.append(r)
+                    lens.append(int(cnt[r]) - 1)
+                else:
+                    ids.append(r)
+                    lens.append(int(cnt[r]))
+            pf.append(len(ids))
+        assert list(rl.row_ids) == ids and list(rl.row_len) == lens and list(rl.portion_first) == pf
+        assert list(rl.row_start) == [int(ptr[r]) for r in ids]

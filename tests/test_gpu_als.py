@@ -410,3 +410,59 @@ def test_recommend_through_master_mirror():
     assert all(r["id"] not in rated and r["predict"] >= 1.0 for r in rec)
     assert all(a["predict"] >= b["predict"] for a, b in zip(rec, rec[1:]))
     m.endTrain()
+
+
+def _host_rowset_arrays(m, step):
+    """What the host front end hands to ycnr_rowset_create for a whole step."""
+    from tests.helpers import step_csr  # noqa: F401
+    csr = m._csr(step)
+    pto = np.asarray(m.portionsRowIdTo[step], np.int32)
+    rl = fe.build_rowlist(csr, pto)
+    return csr, rl
+
+
+@pytest.mark.parametrize("shape,kw", [("ml-100k", {}), ("sparse", dict(users=3000, items=400, ratings=9000))])
+def test_device_ingest_matches_host_front_end_bitwise(shape, kw):
+    """the device-built fetch (by user: compaction; by item: stable counting sort) and portion
+    headers (quirk Q2) equal the host front end's arrays bit for bit, for all four step types; the planner's
+    per-row counts too.  'sparse' has users/items without ratings in a set, 1-rating rows and tiny portions."""
+    if shape == "sparse":
+        table = fe.synth_table("ml-100k", seed=77, **kw)
+        opts = {"factorsCount": 8, "seed": 77, "ratingsInPortionForRmse": 40,
+                "ratingsInPortionForAls": {"byUser": 50, "byItem": 300}}
+    else:
+        table = fe.synth_table(shape)
+        opts = {"factorsCount": 8}
+    m = EmfMaster(table, opts)
+    m.splitDataForTrain()
+    ctx = native.Context(8, table.users, table.items)
+    ctx.table_upload(table.user_ptr, table.item_ids, table.ratings, table.dataset_type)
+    all_sets = (1 << fe.TRAIN) | (1 << fe.VALIDATE) | (1 << fe.TEST)
+    assert (ctx.table_counts(all_sets, False) == table.counts_per_user()).all()
+    assert (ctx.table_counts(all_sets, True) == table.counts_per_item()).all()
+    from you_can_not_recommend_b200.emf_master import STEP_MASK
+    for step in ("byUser", "byItem", "rmseValidate", "rmseTest"):
+        csr, rl = _host_rowset_arrays(m, step)
+        rid = ctx.rowset_from_table(native.STEP_TYPES[step], STEP_MASK[step], m.portionsRowIdTo[step])
+        got = ctx.rowset_read(rid)
+        assert len(got["indx"]) == csr.nnz
+        assert (got["indx"] == csr.idx).all() and (got["vals"] == csr.vals).all(), step
+        assert (got["row_ids"] == rl.row_ids).all() and (got["row_len"] == rl.row_len).all(), step
+        assert (got["row_start"] == rl.row_start).all() and (got["portion_first"] == rl.portion_first).all(), step
+        ctx.rowset_destroy(rid)
+    ctx.close()
+
+
+def test_device_ingest_trains_identically():
+    """One ALS iteration from device-built row sets equals the host-built bulk path bitwise."""
+    prob = make_problem("ml-100k", k=20)
+    outs = []
+    for dev in (False, True):
+        m = EmfMaster(prob["table"], {"factorsCount": 20, "seed": prob["seed"], "gpu": {"bulk": True, "deviceIngest": dev}})
+        m.prepareToTrain(prob["U0"].copy(), prob["V0"].copy())
+        h = m.trainIter()
+        m.syncFactorsToHost()
+        outs.append((h, m.userFactors.copy(), m.itemFactors.copy()))
+        m.endTrain()
+    assert outs[0][0] == outs[1][0]
+    assert (outs[0][1] == outs[1][1]).all() and (outs[0][2] == outs[1][2]).all()

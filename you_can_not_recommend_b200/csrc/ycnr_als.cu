@@ -17,6 +17,7 @@
 #include "gram_tc.cuh"
 #include "portion_kernels.cuh"
 #include "recommend_kernels.cuh"
+#include "ingest_kernels.cuh"
 #include "rmse_kernels.cuh"
 
 #ifndef YCNR_REDUCE_TPT
@@ -274,6 +275,18 @@ struct ycnr_ctx {
   int64_t fac_rows[2] = {0, 0};
   std::vector<void*> peers[2];
   std::vector<RowSet> rowsets;
+  // device-resident ratings table (ycnr_table_upload): user_ptr i64[users+1] | item i32 | rating f32 | dt i8 | elem_user i32
+  struct {
+    DevBuf buf;
+    int64_t nnz = 0;
+    const int64_t* user_ptr = nullptr;
+    const int32_t* item = nullptr;
+    const float* rating = nullptr;
+    const int8_t* dt = nullptr;
+    const int32_t* elem_user = nullptr;
+    bool loaded = false;
+  } table;
+  DevBuf ingest_tmp;
   DevBuf partial;      // split-row tile partials
   DevBuf gather_tmp;   // ycnr_s_als_build_sub_fixed_facts
   Slot slots[kSlots];
@@ -918,6 +931,8 @@ int ycnr_destroy(ycnr_ctx* c) {
   }
   c->partial.release();
   c->gather_tmp.release();
+  c->table.buf.release();
+  c->ingest_tmp.release();
   for (auto& r : c->pinned) cudaHostUnregister((void*)r.first);
   if (c->copied) cudaEventDestroy(c->copied);
   for (auto e : c->chunk_ev) if (e) cudaEventDestroy(e);
@@ -1339,6 +1354,251 @@ int ycnr_set_peers(ycnr_ctx* c, int32_t which, int32_t n, void* const* ptrs) {
   OK(set_device(c));
   CU(cudaStreamSynchronize(c->stream));
   c->peers[which].assign(ptrs, ptrs + n);
+  return 0;
+}
+
+// ---- device-side front end (ingest) ------------------------------------------------------------
+namespace {
+
+// exclusive scan of n int32 values into out[n + 1] (int64); scratch: block sums
+int device_scan(ycnr_ctx* c, const int32_t* d_v, int n, int64_t* d_out, int64_t* d_block_sums) {
+  if (n <= 0) {
+    CU(cudaMemsetAsync(d_out, 0, sizeof(int64_t), c->stream));
+    return 0;
+  }
+  const int nb = (n + ycnr::kScanRowsPerBlock - 1) / ycnr::kScanRowsPerBlock;
+  ycnr::scan_block_sums_kernel<<<nb, ycnr::kScanThreads, 0, c->stream>>>(d_v, n, d_block_sums);
+  ycnr::header_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(d_block_sums, nb);
+  ycnr::scan_apply_kernel<<<nb, ycnr::kScanThreads, 0, c->stream>>>(d_v, n, d_block_sums, d_out);
+  CU(cudaGetLastError());
+  c->prof.launches[YCNR_K_GATHER] += 3;
+  c->prof.total_launches += 3;
+  return 0;
+}
+
+size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+}  // namespace
+
+int ycnr_table_upload(ycnr_ctx* c, const int64_t* user_ptr, const int32_t* item_ids, const float* ratings,
+                      const int8_t* dataset_type) {
+  if (!c || !user_ptr || !item_ids || !ratings || !dataset_type) return fail("ycnr_table_upload: null argument");
+  const int users = (int)c->fac_rows[0], items = (int)c->fac_rows[1];
+  if (user_ptr[0] != 0) return fail("ycnr_table_upload: user_ptr[0] must be 0");
+  for (int u = 0; u < users; ++u)
+    if (user_ptr[u + 1] < user_ptr[u]) return fail("ycnr_table_upload: user_ptr not monotone at %d", u);
+  const int64_t nnz = user_ptr[users];
+  for (int64_t e = 0; e < nnz; ++e) {
+    if (item_ids[e] < 0 || item_ids[e] >= items) return fail("ycnr_table_upload: item id %d out of range", item_ids[e]);
+    if (dataset_type[e] < 0 || dataset_type[e] > 31) return fail("ycnr_table_upload: dataset_type %d out of range", (int)dataset_type[e]);
+  }
+  OK(set_device(c));
+  const size_t o_item = al16((size_t)(users + 1) * 8), o_rat = al16(o_item + (size_t)nnz * 4);
+  const size_t o_dt = al16(o_rat + (size_t)nnz * 4), o_eu = al16(o_dt + (size_t)nnz), total = al16(o_eu + (size_t)nnz * 4);
+  OK(c->table.buf.ensure(total));
+  char* d = (char*)c->table.buf.p;
+  CU(cudaMemcpyAsync(d, user_ptr, (size_t)(users + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  if (nnz) {
+    CU(cudaMemcpyAsync(d + o_item, item_ids, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + o_rat, ratings, (size_t)nnz * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + o_dt, dataset_type, (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+  }
+  c->table.nnz = nnz;
+  c->table.user_ptr = (const int64_t*)d;
+  c->table.item = (const int32_t*)(d + o_item);
+  c->table.rating = (const float*)(d + o_rat);
+  c->table.dt = (const int8_t*)(d + o_dt);
+  c->table.elem_user = (const int32_t*)(d + o_eu);
+  {
+    ProfScope ps(c, YCNR_K_GATHER, users, nnz);
+    ycnr::fill_elem_user_kernel<<<(users + 7) / 8, 256, 0, c->stream>>>(c->table.user_ptr, users, (int32_t*)(d + o_eu));
+  }
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));   // host sources may be freed by the caller on return
+  c->table.loaded = true;
+  return 0;
+}
+
+int ycnr_table_counts(ycnr_ctx* c, uint32_t set_mask, int32_t by_item, int32_t* counts_out) {
+  if (!c || !counts_out) return fail("ycnr_table_counts: null argument");
+  if (!c->table.loaded) return fail("ycnr_table_counts: call ycnr_table_upload first");
+  OK(set_device(c));
+  const int users = (int)c->fac_rows[0], items = (int)c->fac_rows[1];
+  const int n = by_item ? items : users;
+  OK(c->ingest_tmp.ensure((size_t)n * 4));
+  int32_t* d_cnt = (int32_t*)c->ingest_tmp.p;
+  {
+    ProfScope ps(c, YCNR_K_GATHER, n, c->table.nnz);
+    if (by_item) {
+      CU(cudaMemsetAsync(d_cnt, 0, (size_t)n * 4, c->stream));
+      const int grid = (int)std::min<int64_t>((c->table.nnz + 255) / 256 + 1, (int64_t)c->num_sms * 16);
+      ycnr::count_by_item_kernel<<<grid, 256, 0, c->stream>>>(c->table.item, c->table.dt, set_mask, c->table.nnz, d_cnt);
+    } else {
+      ycnr::count_by_user_kernel<<<(users + 7) / 8, 256, 0, c->stream>>>(c->table.user_ptr, c->table.dt, set_mask, users, d_cnt);
+    }
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(counts_out, d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ycnr_rowset_from_table(ycnr_ctx* c, int32_t step_type, uint32_t set_mask, const int32_t* portions_row_id_to,
+                           int32_t n_portions, int32_t* out) {
+  if (!c || !out || n_portions < 0 || (n_portions && !portions_row_id_to)) return fail("ycnr_rowset_from_table: bad argument");
+  if (step_type < YCNR_BY_USER || step_type > YCNR_RMSE_TEST) return fail("ycnr_rowset_from_table: bad stepType");
+  if (!c->table.loaded) return fail("ycnr_rowset_from_table: call ycnr_table_upload first");
+  OK(set_device(c));
+  const int users = (int)c->fac_rows[0], items = (int)c->fac_rows[1];
+  const bool by_item = step_type == YCNR_BY_ITEM;
+  const int rows = by_item ? items : users;
+  for (int p = 0; p < n_portions; ++p) {
+    const int lo = p ? portions_row_id_to[p - 1] : 0;
+    if (portions_row_id_to[p] < lo || portions_row_id_to[p] > rows) return fail("ycnr_rowset_from_table: portion bounds not monotone in [0, rows]");
+  }
+  const int64_t nnz_t = c->table.nnz;
+  const int P = std::max(n_portions, 1);
+  const int n_chunks = (int)((nnz_t + ycnr::kItemChunk - 1) / ycnr::kItemChunk);
+  // scratch: cnt i32[rows] | ptr i64[rows+1] | block sums | pto | last_row | drop_last | flag | len | pos i64[rows+1]
+  //          | (by item) chunk counters i32[n_chunks][items]
+  const int nb = (rows + ycnr::kScanRowsPerBlock - 1) / ycnr::kScanRowsPerBlock + 2;
+  size_t o = 0;
+  const size_t o_cnt = o;   o = al16(o + (size_t)rows * 4);
+  const size_t o_ptr = o;   o = al16(o + (size_t)(rows + 1) * 8);
+  const size_t o_bs = o;    o = al16(o + (size_t)nb * 8);
+  const size_t o_pto = o;   o = al16(o + (size_t)P * 4);
+  const size_t o_last = o;  o = al16(o + (size_t)P * 4);
+  const size_t o_drop = o;  o = al16(o + (size_t)P * 4);
+  const size_t o_flag = o;  o = al16(o + (size_t)rows * 4);
+  const size_t o_len = o;   o = al16(o + (size_t)rows * 4);
+  const size_t o_pos = o;   o = al16(o + (size_t)(rows + 1) * 8);
+  const size_t o_cur = o;   o = al16(o + (by_item ? (size_t)n_chunks * items * 4 : 0));
+  OK(c->ingest_tmp.ensure(o));
+  char* t = (char*)c->ingest_tmp.p;
+  int32_t* d_cnt = (int32_t*)(t + o_cnt);
+  int64_t* d_ptr = (int64_t*)(t + o_ptr);
+  int64_t* d_bs = (int64_t*)(t + o_bs);
+  int32_t* d_pto = (int32_t*)(t + o_pto);
+  int32_t* d_last = (int32_t*)(t + o_last);
+  int32_t* d_drop = (int32_t*)(t + o_drop);
+  int32_t* d_flag = (int32_t*)(t + o_flag);
+  int32_t* d_len = (int32_t*)(t + o_len);
+  int64_t* d_pos = (int64_t*)(t + o_pos);
+  int32_t* d_cur = (int32_t*)(t + o_cur);
+  if (n_portions) CU(cudaMemcpyAsync(d_pto, portions_row_id_to, (size_t)n_portions * 4, cudaMemcpyHostToDevice, c->stream));
+
+  ProfScope ps(c, YCNR_K_GATHER, rows, nnz_t);
+  // 1. row lengths of the fetch and its row pointer
+  if (by_item) {
+    CU(cudaMemsetAsync(d_cur, 0, (size_t)n_chunks * items * 4, c->stream));
+    if (n_chunks) ycnr::item_hist_kernel<<<n_chunks, 256, 0, c->stream>>>(c->table.item, c->table.dt, set_mask, nnz_t, items, d_cur);
+    ycnr::item_chunk_offsets_kernel<<<(items + 255) / 256, 256, 0, c->stream>>>(d_cur, n_chunks, items, d_cnt);
+  } else {
+    ycnr::count_by_user_kernel<<<(users + 7) / 8, 256, 0, c->stream>>>(c->table.user_ptr, c->table.dt, set_mask, users, d_cnt);
+  }
+  CU(cudaGetLastError());
+  OK(device_scan(c, d_cnt, rows, d_ptr, d_bs));
+  int64_t span = 0;
+  CU(cudaMemcpyAsync(&span, d_ptr + rows, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+
+  int id = -1;
+  for (size_t i = 0; i < c->rowsets.size(); ++i)
+    if (!c->rowsets[i].used) { id = (int)i; break; }
+  if (id < 0) { c->rowsets.emplace_back(); id = (int)c->rowsets.size() - 1; }
+  RowSet& rs = c->rowsets[id];
+  rs = RowSet();
+  rs.used = true;
+  rs.step_type = step_type;
+  rs.span = span;
+  rs.n_portions = P;
+  // 2. the fetch itself
+  const size_t o_vals = al16((size_t)span * 4);
+  OK(rs.ratings.ensure(o_vals + al16((size_t)span * 4) + 16));
+  char* dr = (char*)rs.ratings.p;
+  if (by_item) {
+    if (n_chunks)
+      ycnr::item_scatter_kernel<<<n_chunks, 32, 0, c->stream>>>(c->table.item, c->table.rating, c->table.dt, c->table.elem_user,
+                                                               set_mask, nnz_t, items, d_cur, d_ptr, (int32_t*)dr, (float*)(dr + o_vals));
+  } else {
+    ycnr::fill_by_user_kernel<<<(users + 7) / 8, 256, 0, c->stream>>>(c->table.user_ptr, c->table.item, c->table.rating, c->table.dt,
+                                                                     set_mask, users, d_ptr, (int32_t*)dr, (float*)(dr + o_vals));
+  }
+  CU(cudaGetLastError());
+  // 3. portion headers with quirk Q2
+  int32_t pto_all[1] = {rows};
+  if (!n_portions) CU(cudaMemcpyAsync(d_pto, pto_all, 4, cudaMemcpyHostToDevice, c->stream));   // one portion: everything
+  ycnr::portion_tail_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(d_ptr, d_pto, P, d_last, d_drop);
+  ycnr::row_emit_kernel<<<(rows + 255) / 256, 256, 0, c->stream>>>(d_ptr, rows, d_pto, P, d_last, d_drop, d_flag, d_len);
+  CU(cudaGetLastError());
+  OK(device_scan(c, d_flag, rows, d_pos, d_bs));
+  int64_t n_rows64 = 0;
+  CU(cudaMemcpyAsync(&n_rows64, d_pos + rows, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const int n_rows = (int)n_rows64;
+  rs.n_rows = n_rows;
+  const size_t o_ids = al16((size_t)n_rows * 8), o_rl = al16(o_ids + (size_t)n_rows * 4), o_pf = al16(o_rl + (size_t)n_rows * 4);
+  OK(rs.rows.ensure(al16(o_pf + (size_t)(P + 1) * 4) + 16));
+  char* d = (char*)rs.rows.p;
+  ycnr::row_scatter_kernel<<<(rows + 255) / 256, 256, 0, c->stream>>>(d_ptr, rows, d_flag, d_len, d_pos, (int32_t*)(d + o_ids),
+                                                                    (int64_t*)d, (int32_t*)(d + o_rl));
+  ycnr::portion_first_kernel<<<(P + 1 + 255) / 256, 256, 0, c->stream>>>(d_pos, rows, d_pto, P, (int32_t*)(d + o_pf));
+  CU(cudaGetLastError());
+  c->prof.launches[YCNR_K_GATHER] += 6;
+  c->prof.total_launches += 6;
+  rs.view.row_start = (const int64_t*)d;
+  rs.view.row_ids = (const int32_t*)(d + o_ids);
+  rs.view.row_len = (const int32_t*)(d + o_rl);
+  rs.d_portion_first = (const int32_t*)(d + o_pf);
+  rs.view.indx = (const int32_t*)dr;
+  rs.view.vals = (const float*)(dr + o_vals);
+  // 4. the launch plan is built on the host from the emitted row lengths (one small copy each way)
+  std::vector<int32_t> h_len((size_t)std::max(n_rows, 1));
+  if (n_rows) CU(cudaMemcpyAsync(h_len.data(), d + o_rl, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  int64_t nnz = 0;
+  for (int r = 0; r < n_rows; ++r) nnz += h_len[r];
+  rs.nnz = nnz;
+  if (step_type < YCNR_RMSE_VALIDATE) {
+    const PlanCfg cfg{c->dual_max, c->split_cols, c->fused_max};
+    plan_count(h_len.data(), 1, n_rows, cfg, rs.dplan);
+    std::vector<int32_t> packed(rs.dplan.words + 1);
+    plan_fill(h_len.data(), 1, n_rows, cfg, rs.dplan, packed.data(), c->opts.solve_chunks);
+    OK(rs.plan.ensure(packed.size() * 4));
+    CU(cudaMemcpyAsync(rs.plan.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  } else {
+    OK(rs.sums.ensure(((size_t)2 * n_rows + 3 * (size_t)P + 4) * sizeof(double)));
+  }
+  *out = id;
+  return 0;
+}
+
+int ycnr_rowset_info(ycnr_ctx* c, int32_t id, int32_t* n_rows, int64_t* span, int32_t* n_portions) {
+  if (!c || id < 0 || id >= (int)c->rowsets.size() || !c->rowsets[id].used) return fail("ycnr_rowset_info: bad id");
+  const RowSet& rs = c->rowsets[id];
+  if (n_rows) *n_rows = rs.n_rows;
+  if (span) *span = rs.span;
+  if (n_portions) *n_portions = rs.n_portions;
+  return 0;
+}
+
+int ycnr_rowset_read(ycnr_ctx* c, int32_t id, int32_t* row_ids, int64_t* row_start, int32_t* row_len,
+                     int32_t* portion_first, int32_t* indx, float* vals) {
+  if (!c || id < 0 || id >= (int)c->rowsets.size() || !c->rowsets[id].used) return fail("ycnr_rowset_read: bad id");
+  const RowSet& rs = c->rowsets[id];
+  OK(set_device(c));
+  CU(cudaStreamSynchronize(c->stream));
+  if (rs.n_rows) {
+    if (row_ids) CU(cudaMemcpy(row_ids, rs.view.row_ids, (size_t)rs.n_rows * 4, cudaMemcpyDeviceToHost));
+    if (row_start) CU(cudaMemcpy(row_start, rs.view.row_start, (size_t)rs.n_rows * 8, cudaMemcpyDeviceToHost));
+    if (row_len) CU(cudaMemcpy(row_len, rs.view.row_len, (size_t)rs.n_rows * 4, cudaMemcpyDeviceToHost));
+  }
+  if (portion_first) CU(cudaMemcpy(portion_first, rs.d_portion_first, (size_t)(rs.n_portions + 1) * 4, cudaMemcpyDeviceToHost));
+  if (rs.span) {
+    if (indx) CU(cudaMemcpy(indx, rs.view.indx, (size_t)rs.span * 4, cudaMemcpyDeviceToHost));
+    if (vals) CU(cudaMemcpy(vals, rs.view.vals, (size_t)rs.span * 4, cudaMemcpyDeviceToHost));
+  }
   return 0;
 }
 

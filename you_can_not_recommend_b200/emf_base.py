@@ -37,7 +37,7 @@ def default_options():
         "shared": {"userFactorsShmKey": -1, "itemFactorsShmKey": -1, "portionBufferShmKeys": {}},
         # --- additions of the B200 path (not in the reference) ---
         "gpu": {"device": 0, "gramPath": "auto", "dualMaxCols": -1, "splitCols": 0, "profile": False,
-                "bulk": False, "cachePortions": False, "tcMinCols": 0, "solveChunks": 0},
+                "bulk": False, "cachePortions": False, "tcMinCols": 0, "solveChunks": 0, "deviceIngest": False},
         "seed": front_end.DEFAULT_SEED,
     }
 

@@ -177,8 +177,23 @@ class EmfMaster(EmfBase):
                              "fetched": int(csr.ptr[pto[p]]) - a})
             self.portionCache[step] = bufs
 
+    def prepareBulkOnDevice(self):
+        """gpu.deviceIngest: upload the ratings table once and let the device build every step's fetch and
+        portion headers (ycnr_table_upload / ycnr_rowset_from_table) — the master's SQL fetch + per-rating
+        conversion loop (EmfMaster.js:501-614) for whole steps, bit-identical to the host front end."""
+        t = self.table
+        self.ctx.table_upload(t.user_ptr, t.item_ids, t.ratings, t.dataset_type)
+        for step in ("byUser", "byItem", "rmseValidate", "rmseTest"):
+            assert self.world == 1, "deviceIngest builds whole steps; multi-rank slices use the host front end"
+            pto = np.asarray(self.portionsRowIdTo[step], np.int32)
+            rid = self.ctx.rowset_from_table(native.STEP_TYPES[step], STEP_MASK[step], pto)
+            self.rowsets[step] = rid
+            self.rowlists[step] = None
+
     def prepareBulk(self):
         """Upload every step's portions once as a device-resident row set."""
+        if self.options["gpu"].get("deviceIngest", False):
+            return self.prepareBulkOnDevice()
         for step in ("byUser", "byItem", "rmseValidate", "rmseTest"):
             csr = self._csr(step)
             lo, hi = self.my_portions[step]

@@ -24,7 +24,8 @@ EXPORTS = [
     "ycnr_stream", "ycnr_synchronize", "ycnr_host_register", "ycnr_host_unregister", "ycnr_start_train_step", "ycnr_als_portion", "ycnr_end_train_step",
     "ycnr_start_calc_rmse", "ycnr_rmse_portion", "ycnr_s_als_build_sub_fixed_facts", "ycnr_rowset_create",
     "ycnr_rowset_destroy", "ycnr_als_rowset", "ycnr_rmse_rowset", "ycnr_ipc_export", "ycnr_ipc_import",
-    "ycnr_ipc_close", "ycnr_set_peers", "ycnr_recommend_batch", "ycnr_debug_read_partials", "ycnr_profile_reset", "ycnr_profile_read",
+    "ycnr_ipc_close", "ycnr_set_peers", "ycnr_table_upload", "ycnr_table_counts", "ycnr_rowset_from_table",
+    "ycnr_rowset_info", "ycnr_rowset_read", "ycnr_recommend_batch", "ycnr_debug_read_partials", "ycnr_profile_reset", "ycnr_profile_read",
 ]
 
 
@@ -197,6 +198,39 @@ class Context:
         _check(lib().ycnr_rmse_rowset(self._h, C.c_int32(rowset), C.c_double(shift), totals,
                                       psums.ctypes.data_as(C.POINTER(C.c_double)) if n_portions else None))
         return (totals[0], totals[1], totals[2]), psums
+
+    # -- device-side front end
+    def table_upload(self, user_ptr, item_ids, ratings, dataset_type):
+        assert user_ptr.dtype == np.int64 and item_ids.dtype == np.int32 and ratings.dtype == np.float32
+        assert dataset_type.dtype == np.int8 and len(user_ptr) == self.total_users + 1
+        _check(lib().ycnr_table_upload(self._h, _i64(user_ptr), _i32(item_ids), _f32(ratings),
+                                       dataset_type.ctypes.data_as(C.POINTER(C.c_int8))))
+
+    def table_counts(self, set_mask, by_item):
+        out = np.zeros(self.total_items if by_item else self.total_users, np.int32)
+        _check(lib().ycnr_table_counts(self._h, C.c_uint32(set_mask), C.c_int32(int(by_item)), _i32(out)))
+        return out
+
+    def rowset_from_table(self, step_type, set_mask, portions_row_id_to):
+        pto = np.ascontiguousarray(portions_row_id_to, np.int32)
+        rid = C.c_int32(-1)
+        _check(lib().ycnr_rowset_from_table(self._h, C.c_int32(step_type), C.c_uint32(set_mask),
+                                            _i32(pto) if len(pto) else None, C.c_int32(len(pto)), C.byref(rid)))
+        return rid.value
+
+    def rowset_info(self, rowset):
+        n, span, p = C.c_int32(0), C.c_int64(0), C.c_int32(0)
+        _check(lib().ycnr_rowset_info(self._h, C.c_int32(rowset), C.byref(n), C.byref(span), C.byref(p)))
+        return n.value, span.value, p.value
+
+    def rowset_read(self, rowset):
+        """dict of the row set's device arrays (tests, diagnostics)."""
+        n, span, p = self.rowset_info(rowset)
+        out = {"row_ids": np.zeros(n, np.int32), "row_start": np.zeros(n, np.int64), "row_len": np.zeros(n, np.int32),
+               "portion_first": np.zeros(p + 1, np.int32), "indx": np.zeros(span, np.int32), "vals": np.zeros(span, np.float32)}
+        _check(lib().ycnr_rowset_read(self._h, C.c_int32(rowset), _i32(out["row_ids"]), _i64(out["row_start"]),
+                                      _i32(out["row_len"]), _i32(out["portion_first"]), _i32(out["indx"]), _f32(out["vals"])))
+        return out
 
     # -- multi-GPU
     def ipc_export(self, which):
