@@ -187,6 +187,12 @@ int ycnr_rmse_rowset(ycnr_ctx* ctx, int32_t rowset, double global_avg_shift, dou
  * conversion loop of the master (EmfMaster.js:501-614) for whole steps. */
 int ycnr_table_upload(ycnr_ctx* ctx, const int64_t* user_ptr, const int32_t* item_ids, const float* ratings,
                       const int8_t* dataset_type);
+/* First-time split of every user's ratings into train(1) / validate(2) / test(3) on the device, rule and order of
+ * EmfLord.doSplitToSets' JS path (EmfLord.js:450-473) with Math.random() replaced by the library's counter-based
+ * PRNG (seed, user, step) — the same bytes as ycnr_split_sets of the host front end (include/ycnr_host.h).
+ * pcts = dataSetDistr.  Rewrites the uploaded table's dataset_type column; dataset_type_out (may be NULL)
+ * receives it. */
+int ycnr_table_split(ycnr_ctx* ctx, uint64_t seed, const int32_t pcts[3], int8_t* dataset_type_out);
 /* Ratings per user (by_item = 0) or per item (by_item = 1) whose dataset_type bit is set in set_mask —
  * the planner's ratings_count (EmfLord.js:48-128, 255-397).  counts_out[total_users | total_items]. */
 int ycnr_table_counts(ycnr_ctx* ctx, uint32_t set_mask, int32_t by_item, int32_t* counts_out);

@@ -466,3 +466,45 @@ def test_device_ingest_trains_identically():
         m.endTrain()
     assert outs[0][0] == outs[1][0]
     assert (outs[0][1] == outs[1][1]).all() and (outs[0][2] == outs[1][2]).all()
+
+
+@pytest.mark.parametrize("pcts", [(85, 10, 5), (70, 30, 0), (100, 0, 0), (33, 33, 34)])
+def test_device_split_matches_host_split_bitwise(pcts):
+    """the per-user split rule of EmfLord.doSplitToSets (EmfLord.js:450-473) on the device gives
+    the same dataset_type bytes as the host front end (same counter-based PRNG instead of Math.random)."""
+    table = fe.synth_table("ml-100k", seed=123)
+    want = fe.split_sets(table, pcts, seed=999).dataset_type.copy()
+    ctx = native.Context(8, table.users, table.items)
+    ctx.table_upload(table.user_ptr, table.item_ids, table.ratings, np.zeros(table.nnz, np.int8))
+    got = ctx.table_split(999, pcts, table.nnz)
+    assert (got == want).all()
+    cu = ctx.table_counts((1 << fe.TRAIN) | (1 << fe.VALIDATE) | (1 << fe.TEST), False)
+    assert (cu == np.diff(table.user_ptr)).all()          # the uploaded table's column was rewritten too
+    ctx.close()
+
+
+def test_checkpoint_resume_is_bitwise(tmp_path):
+    """EmfManager mirror on the device path: save after one iteration (files written from the device replicas),
+    load into a fresh master and continue — the second iteration equals an uninterrupted run bit for bit."""
+    from you_can_not_recommend_b200.emf_manager import EmfManager
+    prob = make_problem("ml-100k", k=20)
+    opts = {"factorsCount": 20, "seed": prob["seed"], "checkpointEveryIter": True, "gpu": {"bulk": True}}
+    a = EmfMaster(prob["table"], opts)
+    a.prepareToTrain(prob["U0"].copy(), prob["V0"].copy())
+    ha = a.train(2)
+    Ua, Va = a.userFactors.copy(), a.itemFactors.copy()
+    a.endTrain()
+    b = EmfMaster(prob["table"], opts)
+    b.prepareToTrain(prob["U0"].copy(), prob["V0"].copy())
+    EmfManager(b, str(tmp_path / "ml")).train(1)
+    b.endTrain()
+    c = EmfMaster(prob["table"], opts)
+    c.splitDataForTrain()
+    U1, V1, ci = EmfManager(c, str(tmp_path / "ml")).loadCalcResults()
+    assert ci["calcCnt"] == 2 and ci["factorsCount"] == 20      # per-iteration checkpoint + the final save
+    c.prepareToTrain(U1, V1)
+    hc = c.trainIter()
+    c.syncFactorsToHost()
+    assert hc == ha[1]
+    assert (c.userFactors == Ua).all() and (c.itemFactors == Va).all()
+    c.endTrain()

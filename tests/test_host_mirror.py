@@ -63,3 +63,46 @@ def test_master_plan_and_factor_layout():
         a0, b0 = m2[0]._solved_range(s)
         a1, b1 = m2[1]._solved_range(s)
         assert a0 == 0 and b0 == a1 and b1 == (50 if s == "byUser" else m.portionsRowIdTo[s][-1])
+
+
+def test_manager_persistence_roundtrip_cpu(tmp_path):
+    """EmfManager mirror (EmfManager.js:158-191, 324-397, 463-570): raw Float32 row-major factor files +
+    calc_info.json, commit by renaming factors_temp -> factors_ready, reuse rules, grown tables.
+    No GPU involved: a stand-in master carries the fields the manager reads."""
+    import json
+    import numpy as np
+    from you_can_not_recommend_b200.emf_base import default_options
+    from you_can_not_recommend_b200.emf_manager import EmfManager
+
+    class M:
+        pass
+    m = M()
+    m.options = default_options()
+    m.options["gpu"]["bulk"] = False
+    m.ctx = None
+    m.factorsCount, m.totalUsersCount, m.totalItemsCount, m.globalAvgShift = 4, 5, 3, 0.25
+    rng = np.random.default_rng(0)
+    m.userFactors = rng.normal(size=(5, 4)).astype(np.float32)
+    m.itemFactors = rng.normal(size=(3, 4)).astype(np.float32)
+    mgr = EmfManager(m, str(tmp_path / "ml"))
+    assert mgr.loadCalcResults() is None
+    info = mgr.saveCalcResults()
+    ready = tmp_path / "ml_factors_ready"
+    assert sorted(p.name for p in ready.iterdir()) == ["calc_info.json", "item_factors", "user_factors"]
+    assert not (tmp_path / "ml_factors_temp").exists()                       # renamed, not copied
+    assert (ready / "user_factors").stat().st_size == 5 * 4 * 4             # EmfBase.js:694-697: no header
+    assert np.fromfile(ready / "item_factors", np.float32).tobytes() == m.itemFactors.tobytes()
+    ci = json.load(open(ready / "calc_info.json"))
+    assert ci == info and set(ci) == {"alg", "algOptions", "useDoublePrecision", "factorsCount", "dataSetDistr",
+                                      "totalUsersCount", "totalItemsCount", "dbType", "calcDate", "calcCnt",
+                                      "globalAvgShift", "globalBias"}
+    m.globalAvgShift = 0.0
+    U, V, ci2 = mgr.loadCalcResults()
+    assert (U == m.userFactors).all() and (V == m.itemFactors).all() and m.globalAvgShift == 0.25
+    # more users than when the results were stored: old rows kept, new rows from the random init
+    m.totalUsersCount = 7
+    U2, _, _ = mgr.loadCalcResults()
+    assert U2.shape == (7, 4) and (U2[:5] == m.userFactors).all() and np.abs(U2[5:]).max() > 0
+    # different rank: nothing to reuse
+    m.factorsCount = 8
+    assert mgr.loadCalcResults() is None

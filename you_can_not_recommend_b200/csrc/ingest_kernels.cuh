@@ -266,4 +266,55 @@ __global__ void __launch_bounds__(256) portion_first_kernel(const int64_t* __res
   portion_first[p] = (int32_t)pos[min(from, rows)];
 }
 
+// ---- first-time split into train / validate / test ----------------------------------
+// EmfLord.doSplitToSets, JS path (lib/emf/EmfLord.js:450-473), per user with n ratings:
+//   t0 = ceil(n*p0/100), t1 = ceil(n*(p0+p1)/100) - t0, t2 = n - t0 - t1; knuth-shuffle of the user's entries;
+//   the first t0 -> train (1), the next t1 -> validate (2), the rest -> test (3).
+// Upstream shuffles with Math.random(); here, as in the host front end (csrc/host_frontend.cc:208-244),
+// random() = u01(mix64(seed, user, step)) — integer hashing and IEEE double multiply/floor only, so the
+// device reproduces the host's dataset_type bytes exactly.  One thread per user, permutation in scratch.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ uint64_t mix64_dev(uint64_t seed, uint64_t a, uint64_t b) {
+  return splitmix64(splitmix64(splitmix64(seed) + a) + b);
+}
+
+__global__ void __launch_bounds__(128) split_sets_kernel(uint64_t seed, int users, const int64_t* __restrict__ user_ptr,
+                                                         int p0, int p1, int32_t* __restrict__ perm,
+                                                         int8_t* __restrict__ dataset_type) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= users) return;
+  const int64_t beg = user_ptr[u];
+  const int64_t n = user_ptr[u + 1] - beg;
+  if (n <= 0) return;
+  const int64_t t0 = (int64_t)ceil(__dmul_rn((double)n, (double)p0) / 100.0);
+  const int64_t t1 = (int64_t)ceil(__dmul_rn((double)n, (double)(p0 + p1)) / 100.0) - t0;
+  const int64_t t2 = n - (t0 + t1);
+  int64_t c0 = max((int64_t)0, t0), c1 = max((int64_t)0, t1), c2 = max((int64_t)0, t2);
+  if (c0 + c1 + c2 < n) c0 += n - (c0 + c1 + c2);
+  int32_t* pos = perm + beg;
+  for (int64_t i = 0; i < n; ++i) pos[i] = (int32_t)i;
+  int64_t cur = n;
+  uint64_t step = 0;
+  while (cur != 0) {   // knuth-shuffle: r = floor(random() * cur); cur--; swap(a[cur], a[r])
+    const double rnd = __dmul_rn((double)(mix64_dev(seed, (uint64_t)u, step++) >> 11), 1.0 / 9007199254740992.0);
+    const int64_t r = (int64_t)floor(__dmul_rn(rnd, (double)cur));
+    cur -= 1;
+    const int32_t a = pos[cur], b = pos[r];
+    pos[cur] = b;
+    pos[r] = a;
+  }
+  int64_t offs = 0;
+  const int64_t cnts[3] = {c0, c1, c2};
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    for (int64_t i = offs; i < min(n, offs + cnts[s]); ++i) dataset_type[beg + pos[i]] = (int8_t)(s + 1);
+    if (cnts[s]) offs += cnts[s];
+  }
+}
+
 }  // namespace ycnr

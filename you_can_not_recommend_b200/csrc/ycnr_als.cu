@@ -1419,6 +1419,26 @@ int ycnr_table_upload(ycnr_ctx* c, const int64_t* user_ptr, const int32_t* item_
   return 0;
 }
 
+int ycnr_table_split(ycnr_ctx* c, uint64_t seed, const int32_t pcts[3], int8_t* dataset_type_out) {
+  if (!c || !pcts) return fail("ycnr_table_split: null argument");
+  if (!c->table.loaded) return fail("ycnr_table_split: call ycnr_table_upload first");
+  if (pcts[0] < 0 || pcts[1] < 0 || pcts[2] < 0 || pcts[0] + pcts[1] + pcts[2] != 100)
+    return fail("ycnr_table_split: dataSetDistr must be three percentages summing to 100");
+  OK(set_device(c));
+  const int users = (int)c->fac_rows[0];
+  OK(c->ingest_tmp.ensure((size_t)std::max<int64_t>(c->table.nnz, 1) * 4));
+  {
+    ProfScope ps(c, YCNR_K_GATHER, users, c->table.nnz);
+    ycnr::split_sets_kernel<<<(users + 127) / 128, 128, 0, c->stream>>>(seed, users, c->table.user_ptr, pcts[0], pcts[1],
+                                                                      (int32_t*)c->ingest_tmp.p, (int8_t*)c->table.dt);
+  }
+  CU(cudaGetLastError());
+  if (dataset_type_out && c->table.nnz)
+    CU(cudaMemcpyAsync(dataset_type_out, c->table.dt, (size_t)c->table.nnz, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int ycnr_table_counts(ycnr_ctx* c, uint32_t set_mask, int32_t by_item, int32_t* counts_out) {
   if (!c || !counts_out) return fail("ycnr_table_counts: null argument");
   if (!c->table.loaded) return fail("ycnr_table_counts: call ycnr_table_upload first");

@@ -24,7 +24,7 @@ EXPORTS = [
     "ycnr_stream", "ycnr_synchronize", "ycnr_host_register", "ycnr_host_unregister", "ycnr_start_train_step", "ycnr_als_portion", "ycnr_end_train_step",
     "ycnr_start_calc_rmse", "ycnr_rmse_portion", "ycnr_s_als_build_sub_fixed_facts", "ycnr_rowset_create",
     "ycnr_rowset_destroy", "ycnr_als_rowset", "ycnr_rmse_rowset", "ycnr_ipc_export", "ycnr_ipc_import",
-    "ycnr_ipc_close", "ycnr_set_peers", "ycnr_table_upload", "ycnr_table_counts", "ycnr_rowset_from_table",
+    "ycnr_ipc_close", "ycnr_set_peers", "ycnr_table_upload", "ycnr_table_split", "ycnr_table_counts", "ycnr_rowset_from_table",
     "ycnr_rowset_info", "ycnr_rowset_read", "ycnr_recommend_batch", "ycnr_debug_read_partials", "ycnr_profile_reset", "ycnr_profile_read",
 ]
 
@@ -205,6 +205,13 @@ class Context:
         assert dataset_type.dtype == np.int8 and len(user_ptr) == self.total_users + 1
         _check(lib().ycnr_table_upload(self._h, _i64(user_ptr), _i32(item_ids), _f32(ratings),
                                        dataset_type.ctypes.data_as(C.POINTER(C.c_int8))))
+
+    def table_split(self, seed, pcts, nnz):
+        """First-time train/validate/test split on the device; returns the dataset_type column."""
+        out = np.zeros(nnz, np.int8)
+        p = (C.c_int32 * 3)(*[int(x) for x in pcts])
+        _check(lib().ycnr_table_split(self._h, C.c_uint64(seed), p, out.ctypes.data_as(C.POINTER(C.c_int8))))
+        return out
 
     def table_counts(self, set_mask, by_item):
         out = np.zeros(self.total_items if by_item else self.total_users, np.int32)
