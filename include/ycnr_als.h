@@ -196,13 +196,15 @@ int ycnr_table_split(ycnr_ctx* ctx, uint64_t seed, const int32_t pcts[3], int8_t
 /* Ratings per user (by_item = 0) or per item (by_item = 1) whose dataset_type bit is set in set_mask —
  * the planner's ratings_count (EmfLord.js:48-128, 255-397).  counts_out[total_users | total_items]. */
 int ycnr_table_counts(ycnr_ctx* ctx, uint32_t set_mask, int32_t by_item, int32_t* counts_out);
-/* All portions of a step as a device-resident row set, built on the device: the fetch (ratings of the set
+/* The portions of a step as a device-resident row set, built on the device: the fetch (ratings of the set
  * grouped by user in item order, or by item in user order), then the concatenated portion headers for the
- * plan portions_row_id_to[n_portions] (exclusive 0-based upper row bounds, EmfLord.js:510-612) with the
- * conversion loop's quirk (the last rating of every portion is dropped, EmfMaster.js:582-609).  Same result,
- * bit for bit, as ycnr_rowset_create on the host front end's arrays. */
-int ycnr_rowset_from_table(ycnr_ctx* ctx, int32_t step_type, uint32_t set_mask, const int32_t* portions_row_id_to,
-                           int32_t n_portions, int32_t* rowset_out);
+ * plan portions_row_id_to[n_portions] (exclusive 0-based upper row bounds, EmfLord.js:510-612; the first
+ * portion starts at first_row — 0 for a whole step, the previous bound for a rank's slice of the plan) with
+ * the conversion loop's quirk (the last rating of every portion is dropped, EmfMaster.js:582-609).  Same
+ * rows, bit for bit, as ycnr_rowset_create on the host front end's arrays (row_start addresses the whole
+ * step's fetch). */
+int ycnr_rowset_from_table(ycnr_ctx* ctx, int32_t step_type, uint32_t set_mask, int32_t first_row,
+                           const int32_t* portions_row_id_to, int32_t n_portions, int32_t* rowset_out);
 int ycnr_rowset_info(ycnr_ctx* ctx, int32_t rowset, int32_t* n_rows, int64_t* span, int32_t* n_portions);
 /* Copy a row set's arrays back (any pointer may be NULL): row_ids/row_start/row_len[n_rows],
  * portion_first[n_portions+1], indx/vals[span]. */
@@ -230,6 +232,12 @@ int ycnr_recommend_batch(ycnr_ctx* ctx, int32_t n_users, const int32_t* user_ids
                          double global_avg_shift, int32_t* out_item_ids, double* out_predict, int32_t* out_count);
 
 /* ---- diagnostics ------------------------------------------------------------ */
+/* The launch plan the library builds for a row list (host code only, no GPU needed): rows by kernel class.
+ * summary[32]: [0..23] rows per dual bin (tile-row count 1..24), [24] fused rows, [25] split rows, [26] work items
+ * (slices) of the split rows, [27..31] word offsets of the fused list, the split-row list, item_row, item_off and
+ * item_order inside the packed plan; words_out (may be NULL) receives the packed plan (n_words_out words). */
+int ycnr_debug_plan(const ycnr_options* opts, const int32_t* row_len, int32_t n_rows, int32_t* summary,
+                    int32_t* words_out, int64_t cap_words, int64_t* n_words_out);
 /* Copy the tile partials ([items][tiles][16] floats) left by the last split-row launch. */
 int ycnr_debug_read_partials(ycnr_ctx* ctx, float* out, int64_t n_floats);
 

@@ -508,3 +508,35 @@ def test_checkpoint_resume_is_bitwise(tmp_path):
     assert hc == ha[1]
     assert (c.userFactors == Ua).all() and (c.itemFactors == Va).all()
     c.endTrain()
+
+
+def test_device_ingest_rank_slices_match_host_slices():
+    """A rank's slice of the plan built on the device (first_row + its portion bounds) equals the same slice of the
+    host front end's row list, for a 3-way cut of every step (what world_size = 3 would hand out)."""
+    from you_can_not_recommend_b200 import dist as ydist
+    from you_can_not_recommend_b200.emf_master import STEP_MASK
+    table = fe.synth_table("ml-100k", seed=5)
+    m = EmfMaster(table, {"factorsCount": 8, "ratingsInPortionForAls": {"byUser": 3000, "byItem": 3000},
+                          "ratingsInPortionForRmse": 700})
+    m.splitDataForTrain()
+    ctx = native.Context(8, table.users, table.items)
+    ctx.table_upload(table.user_ptr, table.item_ids, table.ratings, table.dataset_type)
+    for step in ("byUser", "byItem", "rmseValidate", "rmseTest"):
+        csr, rl = _host_rowset_arrays(m, step)
+        pto = np.asarray(m.portionsRowIdTo[step], np.int32)
+        cnt = ctx.table_counts(STEP_MASK[step], step == "byItem")
+        assert (cnt == np.diff(csr.ptr)).all()
+        cuts = ydist.balanced_cuts(np.cumsum(cnt, dtype=np.int64)[pto.astype(np.int64) - 1], 3)
+        for r in range(3):
+            lo, hi = int(cuts[r]), int(cuts[r + 1])
+            if hi == lo:
+                continue
+            first_row = 0 if lo == 0 else int(pto[lo - 1])
+            rid = ctx.rowset_from_table(native.STEP_TYPES[step], STEP_MASK[step], pto[lo:hi], first_row)
+            got = ctx.rowset_read(rid)
+            r0, r1 = int(rl.portion_first[lo]), int(rl.portion_first[hi])
+            assert (got["row_ids"] == rl.row_ids[r0:r1]).all() and (got["row_len"] == rl.row_len[r0:r1]).all()
+            assert (got["row_start"] == rl.row_start[r0:r1]).all()
+            assert (got["portion_first"] == rl.portion_first[lo:hi + 1] - r0).all()
+            ctx.rowset_destroy(rid)
+    ctx.close()

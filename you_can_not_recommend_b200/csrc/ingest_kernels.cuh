@@ -193,14 +193,15 @@ __global__ void __launch_bounds__(256) count_by_item_kernel(const int32_t* __res
 }
 
 // ---- portion headers with quirk Q2 (EmfMaster.js:582-609) -----------------------------------------------
-// Portion p covers rows [from_p, to_p) = [pto[p-1], pto[p]).  last_row[p] = its last non-empty row (or -1),
+// Portion p covers rows [from_p, to_p) = [pto[p-1], pto[p]), the first one starts at first_row (a rank's slice
+// of the plan does not start at row 0).  last_row[p] = its last non-empty row (or -1),
 // drop_last[p] = 1 when that row is not emitted (its only rating is the dropped one and it is not alone).
 __global__ void __launch_bounds__(256) portion_tail_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ pto,
-                                                           int n_portions, int32_t* __restrict__ last_row,
+                                                           int n_portions, int first_row, int32_t* __restrict__ last_row,
                                                            int32_t* __restrict__ drop_last) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_portions) return;
-  const int from = p == 0 ? 0 : pto[p - 1], to = pto[p];
+  const int from = p == 0 ? first_row : pto[p - 1], to = pto[p];
   int r = to - 1;
   while (r >= from && ptr[r + 1] == ptr[r]) --r;
   if (r < from) {
@@ -220,14 +221,14 @@ __global__ void __launch_bounds__(256) portion_tail_kernel(const int64_t* __rest
 
 // per row: emitted flag and emitted length
 __global__ void __launch_bounds__(256) row_emit_kernel(const int64_t* __restrict__ ptr, int rows, const int32_t* __restrict__ pto,
-                                                       int n_portions, const int32_t* __restrict__ last_row,
+                                                       int n_portions, int first_row, const int32_t* __restrict__ last_row,
                                                        const int32_t* __restrict__ drop_last, int32_t* __restrict__ flag,
                                                        int32_t* __restrict__ len) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const int64_t c = ptr[r + 1] - ptr[r];
   int f = 0, l = 0;
-  if (c > 0 && n_portions > 0 && r < pto[n_portions - 1]) {
+  if (c > 0 && n_portions > 0 && r >= first_row && r < pto[n_portions - 1]) {
     int lo = 0, hi = n_portions - 1;       // first portion whose upper bound exceeds r
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -259,10 +260,10 @@ __global__ void __launch_bounds__(256) row_scatter_kernel(const int64_t* __restr
 
 // portion_first[p] = number of emitted rows before portion p; portion_first[P] = all of them
 __global__ void __launch_bounds__(256) portion_first_kernel(const int64_t* __restrict__ pos, int rows, const int32_t* __restrict__ pto,
-                                                            int n_portions, int32_t* __restrict__ portion_first) {
+                                                            int n_portions, int first_row, int32_t* __restrict__ portion_first) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p > n_portions) return;
-  const int from = p == 0 ? 0 : pto[p - 1];
+  const int from = p == 0 ? first_row : pto[p - 1];   // rows before first_row are never emitted: pos[first_row] = 0
   portion_first[p] = (int32_t)pos[min(from, rows)];
 }
 

@@ -214,6 +214,22 @@ void plan_fill(const int32_t* len, int stride, int n_rows, const PlanCfg& cfg, D
   }
 }
 
+// Row-class thresholds from the options (shared by ycnr_create and the CPU-only planner diagnostics)
+PlanCfg derive_plan_cfg(const ycnr_options& o, bool* use_tc_out) {
+  const int k = o.factors_count;
+  const int dflt_dual = std::min(96, std::max(0, ((k - 1) / 4) * 4));
+  PlanCfg cfg;
+  cfg.dual_max = o.dual_max_cols < 0 ? dflt_dual : std::min(96, o.dual_max_cols);
+  cfg.split_cols = o.split_cols > 0 ? std::max(o.split_cols, ycnr::kStageRows) : 4096;
+  if (cfg.dual_max > cfg.split_cols) cfg.dual_max = cfg.split_cols;
+  // AUTO: tensor cores whenever the rhs column fits the M = 128 accumulator and rows are 16-byte aligned
+  const bool use_tc = o.gram_path == YCNR_GRAM_TC3XTF32 ||
+                      (o.gram_path == YCNR_GRAM_AUTO && (k & 3) == 0 && k <= 124 && k >= 16);
+  cfg.fused_max = use_tc ? (o.tc_min_cols > 0 ? o.tc_min_cols - 1 : 0) : cfg.split_cols;
+  if (use_tc_out) *use_tc_out = use_tc;
+  return cfg;
+}
+
 struct RowSet {
   bool used = false;
   int step_type = 0;
@@ -602,8 +618,7 @@ struct StagedPortion {
   Slot* slot = nullptr;
 };
 
-int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals, bool with_plan,
-                  StagedPortion& s) {
+int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals, StagedPortion& s) {
   const int R = rows[0];
   if (R < 0) return fail("portion header: negative row count");
   s.n_rows = R;
@@ -617,10 +632,9 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
   s.ratings = off;
   if (R > 0) { s.first_row = rows[1]; s.last_row = rows[1 + 2 * (size_t)(R - 1)]; }
   const PlanCfg cfg{c->dual_max, c->split_cols, c->fused_max};
-  if (with_plan) plan_count(hdr_len, 2, R, cfg, s.plan);
-  const size_t pw = with_plan ? s.plan.words : 0;
+  plan_count(hdr_len, 2, R, cfg, s.plan);
+  const size_t pw = s.plan.words;
   // layout (16-byte aligned sections): start[R] i64 | ids[R] | len[R] | pfirst[2] | plan | indx | vals
-  //                                      | sums f64 [2R+3] (device only: RMSE scratch, never copied)
   auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
   size_t o_start = 0;
   size_t o_ids = al(o_start + (size_t)R * 8);
@@ -630,8 +644,6 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
   size_t o_indx = al(o_plan + pw * 4);
   size_t o_vals = al(o_indx + (size_t)off * 4);
   size_t total = al(o_vals + (size_t)off * 4);
-  size_t o_sums = total;
-  size_t dev_total = with_plan ? total : al(o_sums + (size_t)(2 * R + 3) * 8);
 
   Slot& sl = c->slots[c->next_slot];
   c->next_slot = (c->next_slot + 1) % kSlots;
@@ -660,7 +672,7 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
     CU(cudaMallocHost(&sl.host, want));
     sl.host_cap = want;
   }
-  OK(sl.dev.ensure(dev_total));
+  OK(sl.dev.ensure(total));
   char* h = (char*)sl.host;
   const double tp0 = now_ms();
   {   // header -> row arrays, written in place in the page-locked slot
@@ -675,7 +687,7 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
       h_start[r] = run;
       run += n;
     }
-    if (with_plan) plan_fill(h_len, 1, R, cfg, s.plan, (int32_t*)(h + o_plan), c->opts.solve_chunks);
+    plan_fill(h_len, 1, R, cfg, s.plan, (int32_t*)(h + o_plan), c->opts.solve_chunks);
   }
   int32_t pf[2] = {0, R};
   memcpy(h + o_pf, pf, 8);
@@ -706,7 +718,6 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
   s.view.row_len = (const int32_t*)(d + o_len);
   s.view.indx = (const int32_t*)(d + o_indx);
   s.view.vals = (const float*)(d + o_vals);
-  s.d_sums = (double*)(d + o_sums);
   s.d_pfirst = (const int32_t*)(d + o_pf);
   s.plan_base = (const int32_t*)(d + o_plan);
   s.slot = &sl;
@@ -880,14 +891,12 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   ycnr_ctx* c = new ycnr_ctx();
   c->opts = *o;
   c->k = o->factors_count;
-  const int dflt_dual = std::min(96, std::max(0, ((c->k - 1) / 4) * 4));
-  c->dual_max = o->dual_max_cols < 0 ? dflt_dual : std::min(96, o->dual_max_cols);
-  c->split_cols = o->split_cols > 0 ? std::max(o->split_cols, ycnr::kStageRows) : 4096;
-  if (c->dual_max > c->split_cols) c->dual_max = c->split_cols;
-  // AUTO: tensor cores whenever the rhs column fits the M = 128 accumulator and rows are 16-byte aligned
-  c->use_tc = o->gram_path == YCNR_GRAM_TC3XTF32 ||
-              (o->gram_path == YCNR_GRAM_AUTO && (c->k & 3) == 0 && c->k <= 124 && c->k >= 16);
-  c->fused_max = c->use_tc ? (o->tc_min_cols > 0 ? o->tc_min_cols - 1 : 0) : c->split_cols;
+  bool use_tc = false;
+  const PlanCfg cfg = derive_plan_cfg(*o, &use_tc);
+  c->dual_max = cfg.dual_max;
+  c->split_cols = cfg.split_cols;
+  c->fused_max = cfg.fused_max;
+  c->use_tc = use_tc;
   c->num_sms = prop.multiProcessorCount;
   c->trace = getenv("YCNR_TRACE") != nullptr;
   c->fac_rows[0] = o->total_users;
@@ -1012,6 +1021,10 @@ int ycnr_synchronize(ycnr_ctx* c) {
   if (!c) return fail("ycnr_synchronize: null context");
   OK(set_device(c));
   CU(cudaStreamSynchronize(c->stream));
+  if (c->d2h_pending) {
+    CU(cudaStreamSynchronize(c->d2h_stream));
+    c->d2h_pending = false;
+  }
   return 0;
 }
 
@@ -1058,7 +1071,7 @@ int ycnr_als_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, cons
   const double t0 = now_ms();
   OK(set_device(c));
   StagedPortion s;
-  OK(stage_portion(c, rows, indx, vals, true, s));
+  OK(stage_portion(c, rows, indx, vals, s));
   if (s.n_rows > 0) {
     const double tl0 = now_ms();
     OK(run_als(c, c->step_type, s.view, s.plan, s.plan_base, true));
@@ -1463,8 +1476,8 @@ int ycnr_table_counts(ycnr_ctx* c, uint32_t set_mask, int32_t by_item, int32_t* 
   return 0;
 }
 
-int ycnr_rowset_from_table(ycnr_ctx* c, int32_t step_type, uint32_t set_mask, const int32_t* portions_row_id_to,
-                           int32_t n_portions, int32_t* out) {
+int ycnr_rowset_from_table(ycnr_ctx* c, int32_t step_type, uint32_t set_mask, int32_t first_row,
+                           const int32_t* portions_row_id_to, int32_t n_portions, int32_t* out) {
   if (!c || !out || n_portions < 0 || (n_portions && !portions_row_id_to)) return fail("ycnr_rowset_from_table: bad argument");
   if (step_type < YCNR_BY_USER || step_type > YCNR_RMSE_TEST) return fail("ycnr_rowset_from_table: bad stepType");
   if (!c->table.loaded) return fail("ycnr_rowset_from_table: call ycnr_table_upload first");
@@ -1472,9 +1485,10 @@ int ycnr_rowset_from_table(ycnr_ctx* c, int32_t step_type, uint32_t set_mask, co
   const int users = (int)c->fac_rows[0], items = (int)c->fac_rows[1];
   const bool by_item = step_type == YCNR_BY_ITEM;
   const int rows = by_item ? items : users;
+  if (first_row < 0 || first_row > rows) return fail("ycnr_rowset_from_table: first_row outside [0, rows]");
   for (int p = 0; p < n_portions; ++p) {
-    const int lo = p ? portions_row_id_to[p - 1] : 0;
-    if (portions_row_id_to[p] < lo || portions_row_id_to[p] > rows) return fail("ycnr_rowset_from_table: portion bounds not monotone in [0, rows]");
+    const int lo = p ? portions_row_id_to[p - 1] : first_row;
+    if (portions_row_id_to[p] < lo || portions_row_id_to[p] > rows) return fail("ycnr_rowset_from_table: portion bounds not monotone in [first_row, rows]");
   }
   const int64_t nnz_t = c->table.nnz;
   const int P = std::max(n_portions, 1);
@@ -1548,8 +1562,8 @@ int ycnr_rowset_from_table(ycnr_ctx* c, int32_t step_type, uint32_t set_mask, co
   // 3. portion headers with quirk Q2
   int32_t pto_all[1] = {rows};
   if (!n_portions) CU(cudaMemcpyAsync(d_pto, pto_all, 4, cudaMemcpyHostToDevice, c->stream));   // one portion: everything
-  ycnr::portion_tail_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(d_ptr, d_pto, P, d_last, d_drop);
-  ycnr::row_emit_kernel<<<(rows + 255) / 256, 256, 0, c->stream>>>(d_ptr, rows, d_pto, P, d_last, d_drop, d_flag, d_len);
+  ycnr::portion_tail_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(d_ptr, d_pto, P, first_row, d_last, d_drop);
+  ycnr::row_emit_kernel<<<(rows + 255) / 256, 256, 0, c->stream>>>(d_ptr, rows, d_pto, P, first_row, d_last, d_drop, d_flag, d_len);
   CU(cudaGetLastError());
   OK(device_scan(c, d_flag, rows, d_pos, d_bs));
   int64_t n_rows64 = 0;
@@ -1562,7 +1576,7 @@ int ycnr_rowset_from_table(ycnr_ctx* c, int32_t step_type, uint32_t set_mask, co
   char* d = (char*)rs.rows.p;
   ycnr::row_scatter_kernel<<<(rows + 255) / 256, 256, 0, c->stream>>>(d_ptr, rows, d_flag, d_len, d_pos, (int32_t*)(d + o_ids),
                                                                     (int64_t*)d, (int32_t*)(d + o_rl));
-  ycnr::portion_first_kernel<<<(P + 1 + 255) / 256, 256, 0, c->stream>>>(d_pos, rows, d_pto, P, (int32_t*)(d + o_pf));
+  ycnr::portion_first_kernel<<<(P + 1 + 255) / 256, 256, 0, c->stream>>>(d_pos, rows, d_pto, P, first_row, (int32_t*)(d + o_pf));
   CU(cudaGetLastError());
   c->prof.launches[YCNR_K_GATHER] += 6;
   c->prof.total_launches += 6;
@@ -1690,6 +1704,29 @@ int ycnr_recommend_batch(ycnr_ctx* c, int32_t n_users, const int32_t* user_ids, 
 }
 
 // ---- diagnostics -----------------------------------------------------------------------------
+int ycnr_debug_plan(const ycnr_options* o, const int32_t* row_len, int32_t n_rows, int32_t* summary, int32_t* words_out,
+                    int64_t cap_words, int64_t* n_words_out) {
+  if (!o || (n_rows && !row_len) || n_rows < 0 || !summary) return fail("ycnr_debug_plan: bad argument");
+  const PlanCfg cfg = derive_plan_cfg(*o, nullptr);
+  DevPlan p;
+  plan_count(row_len, 1, n_rows, cfg, p);
+  for (int b = 0; b < kDualBins; ++b) summary[b] = p.n_dual[b];
+  summary[24] = p.n_fused;
+  summary[25] = p.n_multi;
+  summary[26] = p.n_items;
+  summary[27] = (int32_t)p.off_fused;
+  summary[28] = (int32_t)p.off_multi;
+  summary[29] = (int32_t)p.off_item_row;
+  summary[30] = (int32_t)p.off_item_off;
+  summary[31] = (int32_t)p.off_item_order;
+  if (n_words_out) *n_words_out = (int64_t)p.words;
+  if (words_out) {
+    if (cap_words < (int64_t)p.words) return fail("ycnr_debug_plan: %lld words needed, %lld given", (long long)p.words, (long long)cap_words);
+    plan_fill(row_len, 1, n_rows, cfg, p, words_out, o->solve_chunks);
+  }
+  return 0;
+}
+
 int ycnr_debug_read_partials(ycnr_ctx* c, float* out, int64_t n_floats) {
   if (!c || !out || n_floats < 0) return fail("ycnr_debug_read_partials: bad argument");
   OK(set_device(c));

@@ -113,8 +113,10 @@ class EmfMaster(EmfBase):
         else:
             self.createSharedFactors()
             self.initSharedFactorsRandom()
-        for step in ("byUser", "byItem", "rmseValidate", "rmseTest"):
-            self.my_portions[step] = self._slice_portions(step)
+        device_front_end = o["gpu"]["bulk"] and o["gpu"].get("deviceIngest", False)
+        if not device_front_end:                 # (the device front end cuts the slices from its own counts)
+            for step in ("byUser", "byItem", "rmseValidate", "rmseTest"):
+                self.my_portions[step] = self._slice_portions(step)
         # worker + portion buffers (EmfMaster.js:156-234: Int32[2*maxRows+1], Int32/Float32[maxRatings])
         mra = max(self.maxRatingsInPortion["byUser"], self.maxRatingsInPortion["byItem"])
         mrow = max(self.maxRowsInPortion["byUser"], self.maxRowsInPortion["byItem"])
@@ -184,9 +186,21 @@ class EmfMaster(EmfBase):
         t = self.table
         self.ctx.table_upload(t.user_ptr, t.item_ids, t.ratings, t.dataset_type)
         for step in ("byUser", "byItem", "rmseValidate", "rmseTest"):
-            assert self.world == 1, "deviceIngest builds whole steps; multi-rank slices use the host front end"
             pto = np.asarray(self.portionsRowIdTo[step], np.int32)
-            rid = self.ctx.rowset_from_table(native.STEP_TYPES[step], STEP_MASK[step], pto)
+            if self.world == 1 or len(pto) == 0:
+                self.my_portions[step] = (0, len(pto))
+            else:                                                # nnz-balanced contiguous slice, from the device counts
+                cnt = self.ctx.table_counts(STEP_MASK[step], step == "byItem")
+                ends = np.cumsum(cnt, dtype=np.int64)[pto.astype(np.int64) - 1]
+                cuts = ydist.balanced_cuts(ends, self.world)
+                self.my_portions[step] = (int(cuts[self.rank]), int(cuts[self.rank + 1]))
+            lo, hi = self.my_portions[step]                      # this rank's contiguous slice of the plan
+            first_row = 0 if lo == 0 else int(pto[lo - 1])
+            if hi > lo:
+                rid = self.ctx.rowset_from_table(native.STEP_TYPES[step], STEP_MASK[step], pto[lo:hi], first_row)
+            else:                                                # a rank without portions: an empty row set
+                rid = self.ctx.rowset_from_table(native.STEP_TYPES[step], STEP_MASK[step],
+                                                 np.asarray([first_row], np.int32), first_row)
             self.rowsets[step] = rid
             self.rowlists[step] = None
 

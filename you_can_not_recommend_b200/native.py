@@ -25,7 +25,7 @@ EXPORTS = [
     "ycnr_start_calc_rmse", "ycnr_rmse_portion", "ycnr_s_als_build_sub_fixed_facts", "ycnr_rowset_create",
     "ycnr_rowset_destroy", "ycnr_als_rowset", "ycnr_rmse_rowset", "ycnr_ipc_export", "ycnr_ipc_import",
     "ycnr_ipc_close", "ycnr_set_peers", "ycnr_table_upload", "ycnr_table_split", "ycnr_table_counts", "ycnr_rowset_from_table",
-    "ycnr_rowset_info", "ycnr_rowset_read", "ycnr_recommend_batch", "ycnr_debug_read_partials", "ycnr_profile_reset", "ycnr_profile_read",
+    "ycnr_rowset_info", "ycnr_rowset_read", "ycnr_recommend_batch", "ycnr_debug_plan", "ycnr_debug_read_partials", "ycnr_profile_reset", "ycnr_profile_read",
 ]
 
 
@@ -82,6 +82,28 @@ def _i64(a):
 
 def _f32(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def debug_plan(row_len, factors_count=100, gram_path=GRAM_AUTO, dual_max_cols=-1, split_cols=0, tc_min_cols=0):
+    """The library's launch plan for a row list (CPU only): dict with rows per dual bin, the fused / split row
+    lists, the work items (row, offset) of the split rows and their processing order."""
+    o = Options()
+    o.factors_count, o.gram_path, o.dual_max_cols, o.split_cols, o.tc_min_cols = factors_count, gram_path, dual_max_cols, split_cols, tc_min_cols
+    o.total_users = o.total_items = 1
+    row_len = np.ascontiguousarray(row_len, np.int32)
+    summ = np.zeros(32, np.int32)
+    nw = C.c_int64(0)
+    _check(lib().ycnr_debug_plan(C.byref(o), _i32(row_len), C.c_int32(len(row_len)), _i32(summ), None, C.c_int64(0), C.byref(nw)))
+    words = np.zeros(max(1, nw.value), np.int32)
+    _check(lib().ycnr_debug_plan(C.byref(o), _i32(row_len), C.c_int32(len(row_len)), _i32(summ), _i32(words), C.c_int64(len(words)), C.byref(nw)))
+    n_items, n_multi, n_fused = int(summ[26]), int(summ[25]), int(summ[24])
+    dual, off = [], 0
+    for b in range(24):
+        dual.append(words[off:off + int(summ[b])].copy())
+        off += int(summ[b])
+    return {"dual": dual, "fused": words[summ[27]:summ[27] + n_fused].copy(), "multi": words[summ[28]:summ[28] + n_multi].copy(),
+            "item_row": words[summ[29]:summ[29] + n_items].copy(), "item_off": words[summ[30]:summ[30] + n_items].copy(),
+            "item_order": words[summ[31]:summ[31] + n_items].copy()}
 
 
 def device_count():
@@ -218,10 +240,10 @@ class Context:
         _check(lib().ycnr_table_counts(self._h, C.c_uint32(set_mask), C.c_int32(int(by_item)), _i32(out)))
         return out
 
-    def rowset_from_table(self, step_type, set_mask, portions_row_id_to):
+    def rowset_from_table(self, step_type, set_mask, portions_row_id_to, first_row=0):
         pto = np.ascontiguousarray(portions_row_id_to, np.int32)
         rid = C.c_int32(-1)
-        _check(lib().ycnr_rowset_from_table(self._h, C.c_int32(step_type), C.c_uint32(set_mask),
+        _check(lib().ycnr_rowset_from_table(self._h, C.c_int32(step_type), C.c_uint32(set_mask), C.c_int32(first_row),
                                             _i32(pto) if len(pto) else None, C.c_int32(len(pto)), C.byref(rid)))
         return rid.value
 
