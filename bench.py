@@ -380,6 +380,7 @@ def main():
                        "ratings_in_portion": 10000, "parallelism": "rows nnz-balanced over %d GPU(s)" % world,
                        "replica_refresh": ("peer stores from the solve kernels" if args.fused_peers else "NCCL broadcast per rank slice") if world > 1 else "none",
                        "l2": "inputs_exceed_l2 (CSR + factors >> 126 MB)", "gram_path": args.gram,
+                       "kernels_note": "per-class times are CUDA-event intervals; row sets under 400k rows per rank run their dual bins on three streams, so those intervals overlap and add up to more than the step",
                        "step": "byUser + byItem + 3 RMSE passes"},
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches,

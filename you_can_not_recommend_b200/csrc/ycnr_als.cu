@@ -76,6 +76,7 @@ struct DevBuf {
 // ---- row classification -------------------------------------------------------------
 constexpr int kDualBins = 24;  // one bin per tile-row count mt = ceil(n / 4), n <= 96
 constexpr int kMaxChunks = 8;
+constexpr int kSpreadBulkRows = 400000;
 constexpr int kMinItemsPerChunk = 4 * 148;   // a persistent Gram launch needs a few items per SM
 
 struct PlanCfg {
@@ -313,6 +314,10 @@ struct ycnr_ctx {
   std::vector<std::pair<int32_t, int32_t>> solved_ranges;  // [first,last] row ids per portion
   // YCNR_TRACE=1: host-side time of the per-portion path, printed per step to stderr
   bool trace = false;
+  // Bulk half-steps: dual bins on the bin streams too?  -1 = auto (row sets below kSpreadBulkRows rows: the bins
+  // are then a few waves each; measured on B200: ML-1M shape 1.30 -> 1.04 ms per iteration, MAL 53.2 -> 52.3 ms),
+  // YCNR_SPREAD_BULK=0/1 forces it.  Overlapped launches make the per-class event times overlap as well.
+  int spread_bulk = -1;
   double t_parse = 0, t_slot_wait = 0, t_copy_issue = 0, t_launch = 0;
   int t_portions = 0;
   // profiling
@@ -899,6 +904,7 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   c->use_tc = use_tc;
   c->num_sms = prop.multiProcessorCount;
   c->trace = getenv("YCNR_TRACE") != nullptr;
+  if (const char* e = getenv("YCNR_SPREAD_BULK")) c->spread_bulk = atoi(e) ? 1 : 0;
   c->fac_rows[0] = o->total_users;
   c->fac_rows[1] = o->total_items;
   CU(cudaSetDevice(o->device));
@@ -1303,7 +1309,8 @@ int ycnr_als_rowset(ycnr_ctx* c, int32_t id) {
   OK(ensure_fixed_current(c, 1 - solved));
   OK(ensure_fixed_current(c, solved));
   if (rs.n_rows == 0) return 0;
-  return run_als(c, rs.step_type, rs.view, rs.dplan, (const int32_t*)rs.plan.p);
+  const bool spread = c->spread_bulk < 0 ? rs.n_rows < kSpreadBulkRows : c->spread_bulk != 0;
+  return run_als(c, rs.step_type, rs.view, rs.dplan, (const int32_t*)rs.plan.p, spread);
 }
 
 int ycnr_rmse_rowset(ycnr_ctx* c, int32_t id, double shift, double* totals, double* portion_sums) {
