@@ -14,7 +14,7 @@ typedef struct napi_callback_info__* napi_callback_info;
 typedef enum { napi_ok = 0 } napi_status;
 typedef enum {
   napi_int8_array, napi_uint8_array, napi_uint8_clamped_array, napi_int16_array, napi_uint16_array,
-  napi_int32_array, napi_uint32_array, napi_float32_array, napi_float64_array
+  napi_int32_array, napi_uint32_array, napi_float32_array, napi_float64_array, napi_bigint64_array, napi_biguint64_array
 } napi_typedarray_type;
 typedef napi_value (*napi_callback)(napi_env env, napi_callback_info info);
 typedef void (*napi_finalize)(napi_env env, void* data, void* hint);
@@ -29,6 +29,7 @@ typedef struct napi_module {
 napi_status napi_get_cb_info(napi_env, napi_callback_info, size_t* argc, napi_value* argv, napi_value* this_arg, void** data);
 napi_status napi_get_typedarray_info(napi_env, napi_value, napi_typedarray_type*, size_t* length, void** data, napi_value* arraybuffer, size_t* byte_offset);
 napi_status napi_get_value_int32(napi_env, napi_value, int32_t*);
+napi_status napi_get_value_uint32(napi_env, napi_value, uint32_t*);
 napi_status napi_get_value_double(napi_env, napi_value, double*);
 napi_status napi_get_value_bool(napi_env, napi_value, bool*);
 napi_status napi_get_named_property(napi_env, napi_value object, const char* name, napi_value* result);

@@ -208,6 +208,120 @@ napi_value DAlsBuildSubFixedFacts(napi_env env, napi_callback_info) {
   return nullptr;
 }
 
+// ---- bulk mode: a whole step resident on the device ---------------------------
+// tableUpload(handle, BigInt64Array userPtr, Int32Array itemIds, Float32Array ratings, Int8Array datasetType)
+napi_value TableUpload(napi_env env, napi_callback_info info) {
+  napi_value a[5];
+  ycnr_ctx* c;
+  int64_t* uptr;
+  int32_t* items;
+  float* ratings;
+  int8_t* dt;
+  size_t n0, n1, n2, n3;
+  if (!args(env, info, 5, a) || !handle(env, a[0], &c) || !typed(env, a[1], napi_bigint64_array, &uptr, &n0) ||
+      !typed(env, a[2], napi_int32_array, &items, &n1) || !typed(env, a[3], napi_float32_array, &ratings, &n2) ||
+      !typed(env, a[4], napi_int8_array, &dt, &n3))
+    return nullptr;
+  if (n0 < 1 || n1 != n2 || n1 != n3 || (int64_t)n1 != uptr[n0 - 1]) {
+    fail(env, "tableUpload: array sizes do not match userPtr");
+    return nullptr;
+  }
+  check(env, ycnr_table_upload(c, uptr, items, ratings, dt));
+  return undefined(env);
+}
+
+// tableSplit(handle, seed, p0, p1, p2, Int8Array datasetTypeOut)   (EmfLord.doSplitToSets, EmfLord.js:450-473)
+napi_value TableSplit(napi_env env, napi_callback_info info) {
+  napi_value a[6];
+  ycnr_ctx* c;
+  double seed;
+  int32_t pcts[3];
+  int8_t* out;
+  size_t n;
+  if (!args(env, info, 6, a) || !handle(env, a[0], &c) || napi_get_value_double(env, a[1], &seed) != napi_ok ||
+      napi_get_value_int32(env, a[2], &pcts[0]) != napi_ok || napi_get_value_int32(env, a[3], &pcts[1]) != napi_ok ||
+      napi_get_value_int32(env, a[4], &pcts[2]) != napi_ok || !typed(env, a[5], napi_int8_array, &out, &n))
+    return nullptr;
+  check(env, ycnr_table_split(c, (uint64_t)seed, pcts, out));
+  return undefined(env);
+}
+
+// tableCounts(handle, setMask, byItem, Int32Array countsOut)   (ratings_count per row for splitToPortions)
+napi_value TableCounts(napi_env env, napi_callback_info info) {
+  napi_value a[4];
+  ycnr_ctx* c;
+  uint32_t mask;
+  int32_t by_item, *out;
+  size_t n;
+  if (!args(env, info, 4, a) || !handle(env, a[0], &c) || napi_get_value_uint32(env, a[1], &mask) != napi_ok ||
+      napi_get_value_int32(env, a[2], &by_item) != napi_ok || !typed(env, a[3], napi_int32_array, &out, &n))
+    return nullptr;
+  check(env, ycnr_table_counts(c, mask, by_item, out));
+  return undefined(env);
+}
+
+// rowsetFromTable(handle, stepType, setMask, firstRow, Int32Array portionsRowIdTo) -> rowset id
+napi_value RowsetFromTable(napi_env env, napi_callback_info info) {
+  napi_value a[5];
+  ycnr_ctx* c;
+  int32_t step, first_row, *pto, id = -1;
+  uint32_t mask;
+  size_t n;
+  if (!args(env, info, 5, a) || !handle(env, a[0], &c) || napi_get_value_int32(env, a[1], &step) != napi_ok ||
+      napi_get_value_uint32(env, a[2], &mask) != napi_ok || napi_get_value_int32(env, a[3], &first_row) != napi_ok ||
+      !typed(env, a[4], napi_int32_array, &pto, &n))
+    return nullptr;
+  if (!check(env, ycnr_rowset_from_table(c, step, mask, first_row, pto, (int32_t)n, &id))) return nullptr;
+  napi_value v;
+  napi_create_int32(env, id, &v);
+  return v;
+}
+
+// alsRowset(handle, rowset): one half-step over a resident row set (EmfLord.alsTrainStep, EmfLord.js:963-984)
+napi_value AlsRowset(napi_env env, napi_callback_info info) {
+  napi_value a[2];
+  ycnr_ctx* c;
+  int32_t id;
+  if (!args(env, info, 2, a) || !handle(env, a[0], &c) || napi_get_value_int32(env, a[1], &id) != napi_ok) return nullptr;
+  check(env, ycnr_als_rowset(c, id));
+  return undefined(env);
+}
+
+// rmseRowset(handle, rowset, globalAvgShift, Float64Array portionSums /*[3 * portions]*/) -> {rSumDiff2, rCnt, rSum}
+// portionSums carries the per-portion partials quirk Q7 needs (EmfMaster.js:777-783 uses the LAST portion's).
+napi_value RmseRowset(napi_env env, napi_callback_info info) {
+  napi_value a[4];
+  ycnr_ctx* c;
+  int32_t id, np = 0;
+  double shift, *ps, totals[3];
+  size_t n;
+  if (!args(env, info, 4, a) || !handle(env, a[0], &c) || napi_get_value_int32(env, a[1], &id) != napi_ok ||
+      napi_get_value_double(env, a[2], &shift) != napi_ok || !typed(env, a[3], napi_float64_array, &ps, &n))
+    return nullptr;
+  if (!check(env, ycnr_rowset_info(c, id, nullptr, nullptr, &np))) return nullptr;
+  if (n < (size_t)3 * (size_t)np) {
+    fail(env, "rmseRowset: portionSums needs 3 doubles per portion");
+    return nullptr;
+  }
+  if (!check(env, ycnr_rmse_rowset(c, id, shift, totals, ps))) return nullptr;
+  napi_value o, v;
+  napi_create_object(env, &o);
+  napi_create_double(env, totals[0], &v); napi_set_named_property(env, o, "rSumDiff2", v);
+  napi_create_double(env, totals[1], &v); napi_set_named_property(env, o, "rCnt", v);
+  napi_create_double(env, totals[2], &v); napi_set_named_property(env, o, "rSum", v);
+  return o;
+}
+
+// downloadFactors(handle, which): device replica -> the attached host segment (bulk mode keeps factors on the device)
+napi_value DownloadFactors(napi_env env, napi_callback_info info) {
+  napi_value a[2];
+  ycnr_ctx* c;
+  int32_t which;
+  if (!args(env, info, 2, a) || !handle(env, a[0], &c) || napi_get_value_int32(env, a[1], &which) != napi_ok) return nullptr;
+  check(env, ycnr_download_factors(c, which, 0, -1));
+  return undefined(env);
+}
+
 // hostRegister(handle, typedArray): page-lock a portion-cache buffer (usePortionsCache) for direct DMA
 napi_value HostRegister(napi_env env, napi_callback_info info) {
   napi_value a[2];
@@ -276,6 +390,13 @@ napi_value Init(napi_env env, napi_value exports) {
       {"rmsePortion", nullptr, RmsePortion, nullptr, nullptr, nullptr, 0, nullptr},
       {"sAlsBuildSubFixedFacts", nullptr, SAlsBuildSubFixedFacts, nullptr, nullptr, nullptr, 0, nullptr},
       {"dAlsBuildSubFixedFacts", nullptr, DAlsBuildSubFixedFacts, nullptr, nullptr, nullptr, 0, nullptr},
+      {"tableUpload", nullptr, TableUpload, nullptr, nullptr, nullptr, 0, nullptr},
+      {"tableSplit", nullptr, TableSplit, nullptr, nullptr, nullptr, 0, nullptr},
+      {"tableCounts", nullptr, TableCounts, nullptr, nullptr, nullptr, 0, nullptr},
+      {"rowsetFromTable", nullptr, RowsetFromTable, nullptr, nullptr, nullptr, 0, nullptr},
+      {"alsRowset", nullptr, AlsRowset, nullptr, nullptr, nullptr, 0, nullptr},
+      {"rmseRowset", nullptr, RmseRowset, nullptr, nullptr, nullptr, 0, nullptr},
+      {"downloadFactors", nullptr, DownloadFactors, nullptr, nullptr, nullptr, 0, nullptr},
       {"hostRegister", nullptr, HostRegister, nullptr, nullptr, nullptr, 0, nullptr},
       {"recommend", nullptr, Recommend, nullptr, nullptr, nullptr, 0, nullptr},
       {"destroy", nullptr, Destroy, nullptr, nullptr, nullptr, 0, nullptr},
