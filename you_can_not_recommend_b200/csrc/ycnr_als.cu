@@ -320,6 +320,9 @@ struct ycnr_ctx {
   int spread_bulk = -1;
   double t_parse = 0, t_slot_wait = 0, t_copy_issue = 0, t_launch = 0;
   int t_portions = 0;
+  // kernels whose dynamic shared-memory limit was raised on this context's device (function attributes are
+  // per device: a process-wide flag would skip the second device of a process)
+  std::vector<std::pair<const void*, size_t>> smem_configured;
   // profiling
   std::vector<ProfRec> prof_open;
   std::vector<cudaEvent_t> ev_pool;
@@ -340,6 +343,19 @@ DstList make_dst(ycnr_ctx* c, int which) {
   for (void* p : c->peers[which])
     if (d.n < YCNR_MAX_DST) d.p[d.n++] = (float*)p;
   return d;
+}
+
+int ensure_dynamic_smem(ycnr_ctx* c, const void* func, size_t bytes) {
+  for (auto& e : c->smem_configured)
+    if (e.first == func) {
+      if (e.second >= bytes) return 0;
+      CU(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      e.second = bytes;
+      return 0;
+    }
+  CU(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  c->smem_configured.emplace_back(func, bytes);
+  return 0;
 }
 
 struct ProfScope {
@@ -392,11 +408,7 @@ int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int item_from, int n
     t.variant = (uint32_t)c->opts.tc_variant;
     t.prefetch = pa.fixed_bytes > ((size_t)48 << 20) ? 1 : 0;
     const size_t smem = gram_tc_smem_bytes<KT>();
-    static bool configured = false;
-    if (!configured) {
-      CU(cudaFuncSetAttribute(gram_tc_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
-    }
+    OK(ensure_dynamic_smem(c, reinterpret_cast<const void*>(&gram_tc_kernel<KT>), smem));
     const int grid = std::min(n_items, c->num_sms);
     ProfScope ps(c, YCNR_K_GRAM_TC, n_items, ratings);
     gram_tc_kernel<KT><<<grid, TcCfg<KT>::THREADS, smem, c->stream>>>(t);
@@ -495,11 +507,7 @@ int launch_dual_bin(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t 
   int red = 0;
   for (int mt = 1; mt <= MT_MAX; ++mt) red = std::max(red, dual_red_floats(mt, NT));
   const size_t smem = ((size_t)4 * MT_MAX * a.pitch + (MT_MAX + 1) * 16 + 16 * MT_MAX + 8 * MT_MAX + red) * sizeof(float);
-  static size_t configured = 0;  // per instantiation
-  if (smem > 48 * 1024 && smem > configured) {
-    CU(cudaFuncSetAttribute(als_dual_kernel<MT_MAX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (smem > 48 * 1024) OK(ensure_dynamic_smem(c, reinterpret_cast<const void*>(&als_dual_kernel<MT_MAX, NT>), smem));
   ProfScope ps(c, YCNR_K_DUAL_FUSED, count, ratings, st);
   als_dual_kernel<MT_MAX, NT><<<count, NT, smem, st>>>(a);
   CU(cudaGetLastError());
