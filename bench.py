@@ -125,9 +125,12 @@ def build_table(args):
 
 
 class CpuArm:
-    """The reference's CPU implementation of the path: per-row gather -> sgemm(T,N) -> +lambda*n*I ->
-    sgemv -> sgesv through multi-threaded OpenBLAS (oracle O32), timed on an evenly
-    spread sample of 10k-rating portions of both half-steps and extrapolated linearly to the dataset."""
+    """The reference's CPU implementation of the path: per-row gather -> sgemm(T,N) -> +lambda*n*I -> sgemv -> sgesv
+    (oracle O32 over OpenBLAS) with ALL host threads in the reference's own layout: one worker per
+    core, each working on its own portions with single-threaded BLAS (numThreadsForTrain.als = numCPUs,
+    EmfBase.js:105-110) — measured here 5-10x faster than one worker with a multi-threaded BLAS, whose k x k
+    problems are too small to thread.  Timed on an evenly spread sample of 10k-rating portions of both half-steps
+    and extrapolated linearly to the dataset."""
 
     def __init__(self, table, k):
         from oracle import oracle
@@ -135,7 +138,7 @@ class CpuArm:
         from you_can_not_recommend_b200.emf_master import EmfMaster
         self.oracle, self.fe, self.table, self.k = oracle, fe, table, k
         self.cores = os.cpu_count() or 1
-        self.have_blas = oracle.set_blas(threads=self.cores)
+        self.have_blas = oracle.set_blas(threads=1)
         self.m = EmfMaster(table, {"factorsCount": k})
         self.m.splitDataForTrain()
         self.U = fe.init_factors(table.users, k, 0)
@@ -144,31 +147,40 @@ class CpuArm:
         self.m._csr("byItem")
 
     def sample(self, seconds, offset=0):
+        from concurrent.futures import ThreadPoolExecutor
         m, fe, oracle = self.m, self.fe, self.oracle
         per_rating, desc = {}, []
-        for step in ("byUser", "byItem"):
-            csr = m._csr(step)
-            pto = m.portionsRowIdTo[step]
-            fixed, solved = (self.V, self.U) if step == "byUser" else (self.U, self.V)
-            n_por = len(pto)
-            stride = max(1, n_por // 64)                      # evenly spread over the id range
-            mr, mrow = m.maxRatingsInPortion[step], m.maxRowsInPortion[step] + 1
-            done_r, t_used, used = 0, 0.0, 0
-            p = offset % stride
-            while p < n_por and t_used < seconds / 2:
-                rows, indx, vals, _ = fe.build_portion(csr, 0 if p == 0 else int(pto[p - 1]), int(pto[p]), mrow, mr)
-                t0 = time.perf_counter()
-                done_r += oracle.als_portion(rows, indx, vals, fixed, solved, 0.05, use_blas=self.have_blas)
-                t_used += time.perf_counter() - t0
-                used += 1
-                p += stride
-            per_rating[step] = t_used / max(done_r, 1)
-            desc.append("%s: %d of %d portions (%d ratings, %.1f s)" % (step, used, n_por, done_r, t_used))
+        with ThreadPoolExecutor(self.cores) as pool:
+            for step in ("byUser", "byItem"):
+                csr = m._csr(step)
+                pto = m.portionsRowIdTo[step]
+                fixed, solved = (self.V, self.U) if step == "byUser" else (self.U, self.V)
+                n_por = len(pto)
+                stride = max(1, n_por // (128 * self.cores))     # evenly spread over the id range
+                mr, mrow = m.maxRatingsInPortion[step], m.maxRowsInPortion[step] + 1
+                done_r, t_used, used = 0, 0.0, 0
+                p = offset % stride
+
+                def solve(bufs):
+                    return oracle.als_portion(bufs[0], bufs[1], bufs[2], fixed, solved, 0.05, use_blas=self.have_blas)
+
+                while p < n_por and t_used < seconds / 2:
+                    batch = []                                   # a few portions per worker, converted outside the clock
+                    while p < n_por and len(batch) < 8 * self.cores:
+                        batch.append(fe.build_portion(csr, 0 if p == 0 else int(pto[p - 1]), int(pto[p]), mrow, mr)[:3])
+                        p += stride
+                    t0 = time.perf_counter()
+                    done_r += sum(pool.map(solve, batch))
+                    t_used += time.perf_counter() - t0
+                    used += len(batch)
+                per_rating[step] = t_used / max(done_r, 1)
+                desc.append("%s: %d of %d portions (%d ratings, %.1f s)" % (step, used, n_por, done_r, t_used))
         iter_s = self.nnz12 * (per_rating["byUser"] + per_rating["byItem"])
         return {
             "value": self.table.nnz / iter_s, "unit": UNIT, "cores": self.cores, "kind": "port",
             "sample": "; ".join(desc) + "; extrapolated linearly to %d train+validate ratings; RMSE passes excluded" % self.nnz12,
-            "blas": "openblas(scipy), %d threads" % self.cores if self.have_blas else "portable C loops",
+            "threads": "%d workers x 1 BLAS thread (the reference's numThreadsForTrain.als = numCPUs layout)" % self.cores,
+            "blas": "openblas(scipy)" if self.have_blas else "portable C loops",
             "iter_seconds_extrapolated": iter_s,
         }
 
