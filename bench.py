@@ -106,7 +106,7 @@ def measured_peaks():
 
 def measured_traffic(workload, k, cls):
     """DRAM bytes per launch of kernel class `cls` from the committed ncu --set full capture
-    (profiles/traffic_<workload>.json, written by scripts/gpu_round1_final.sh + DESIGN.md §5); None when
+    (profiles/traffic_<workload>.json, written by scripts/gpu_round_evidence.sh + DESIGN.md §5); None when
     there is no capture for this workload / rank."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic_%s.json" % workload)))

@@ -55,6 +55,45 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _shared_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    ydist.init_from_env("gloo")
+
+    def init(mats):
+        mats[0][...] = 1.0
+        mats[1][...] = 2.0
+
+    U, V = ydist.node_shared_matrices("test_%d" % port, [(6, 3), (4, 3)], rank, init)
+    first = (float(U.sum()), float(V.sum()))               # rank 0's initialisation is visible everywhere
+    a, b = (0, 3) if rank == 0 else (3, 6)
+    U[a:b] = 10.0 * (rank + 1)                              # every rank writes back only the rows it solved
+    dist.barrier()
+    q.put((rank, first, np.array(U).copy(), os.path.exists("/dev/shm/ycnr_test_%d_0" % port)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_node_shared_host_segments_gloo():
+    """Per-portion mode with several ranks on one box: ONE pair of host factor segments (upstream: every worker
+    of a node maps the same SysV segment, EmfBase.js:403-450); a rank's writes are seen by the others without
+    any copy, and the /dev/shm names are gone once everybody has mapped them."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shared_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, first, U, exists in res:
+        assert first == (18.0, 24.0) and not exists
+        assert (U[:3] == 10.0).all() and (U[3:] == 20.0).all()
+
+
 def test_two_rank_exchange_gloo():
     world = 2
     ctx = mp.get_context("spawn")

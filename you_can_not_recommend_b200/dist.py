@@ -128,6 +128,30 @@ def connect_peers(ctx, which, rank, world, group=None):
     return ptrs
 
 
+def node_shared_matrices(tag, shapes, rank, init_fn=None, group=None):
+    """One set of float32 matrices shared by all ranks of the box through /dev/shm, the way every worker of a
+    reference node maps the same SysV segments (EmfBase.js:403-412 create, 430-450 open): rank 0 creates the
+    files and runs init_fn(mats), everybody maps them after a barrier, then the names are unlinked (the
+    mappings stay).  Returns the list of np.memmap arrays."""
+    import numpy as np
+    paths = ["/dev/shm/ycnr_%s_%d" % (tag, i) for i in range(len(shapes))]
+    mats = None
+    if rank == 0:
+        mats = [np.memmap(p, np.float32, "w+", shape=tuple(sh)) for p, sh in zip(paths, shapes)]
+        if init_fn is not None:
+            init_fn(mats)
+        for m_ in mats:
+            m_.flush()
+    barrier(group)
+    if rank != 0:
+        mats = [np.memmap(p, np.float32, "r+", shape=tuple(sh)) for p, sh in zip(paths, shapes)]
+    barrier(group)
+    if rank == 0:            # every rank holds its mapping now: the names can go
+        for p in paths:
+            os.unlink(p)
+    return mats
+
+
 def barrier(group=None):
     import torch.distributed as dist
     dist.barrier(group=group)

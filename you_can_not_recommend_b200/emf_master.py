@@ -232,22 +232,13 @@ class EmfMaster(EmfBase):
         import os
         k = self.factorsCount
         tag = "%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid())
-        self._shm_paths = ["/dev/shm/ycnr_%s_%s" % (tag, n) for n in ("user_factors", "item_factors")]
-        shapes = [(self.totalUsersCount, k), (self.totalItemsCount, k)]
-        if self.rank == 0:
-            mats = [np.memmap(p, np.float32, "w+", shape=sh) for p, sh in zip(self._shm_paths, shapes)]
+
+        def init(mats):
             self.userFactors, self.itemFactors = mats
             self.initSharedFactorsRandom()
-            for m_ in mats:
-                m_.flush()
-        ydist.barrier(self.group)
-        if self.rank != 0:
-            self.userFactors, self.itemFactors = [np.memmap(p, np.float32, "r+", shape=sh)
-                                                  for p, sh in zip(self._shm_paths, shapes)]
-        ydist.barrier(self.group)
-        if self.rank == 0:            # every rank holds its mapping now: the names can go
-            for p in self._shm_paths:
-                os.unlink(p)
+
+        self.userFactors, self.itemFactors = ydist.node_shared_matrices(
+            tag, [(self.totalUsersCount, k), (self.totalItemsCount, k)], self.rank, init, self.group)
         self.sharedHost = True
 
     def endTrain(self):
