@@ -66,6 +66,7 @@ def _shared_worker(rank, world, port, q):
 
     U, V = ydist.node_shared_matrices("test_%d" % port, [(6, 3), (4, 3)], rank, init)
     first = (float(U.sum()), float(V.sum()))               # rank 0's initialisation is visible everywhere
+    dist.barrier()                                          # (nobody writes before everybody has looked)
     a, b = (0, 3) if rank == 0 else (3, 6)
     U[a:b] = 10.0 * (rank + 1)                              # every rank writes back only the rows it solved
     dist.barrier()
