@@ -140,9 +140,12 @@ int ycnr_device_factors(ycnr_ctx* ctx, int32_t which, void** dptr_out);
 int ycnr_stream(ycnr_ctx* ctx, void** cuda_stream_out);
 int ycnr_synchronize(ycnr_ctx* ctx);
 
-/* Page-lock caller memory that holds portion buffers (the shm segments of
- * EmfMaster.createWorkPortionBuffers, EmfMaster.js:156-234).  Portions whose indx/vals lie
- * inside a registered region are DMA'd straight from it instead of being staged. */
+/* Page-lock caller memory that holds CACHED portion buffers (usePortionsCache: the master keeps converted
+ * portions, EmfMaster.js:434-494, 656-658; segments of EmfMaster.createWorkPortionBuffers, EmfMaster.js:156-234).
+ * Portions whose header / indx / vals lie inside a registered region are DMA'd straight from it,
+ * ASYNCHRONOUSLY: such memory must stay unmodified until the step ends (ycnr_end_train_step, or the return of
+ * ycnr_rmse_portion).  Buffers that are refilled between portions (the upstream work buffer) must NOT be
+ * registered: unregistered buffers are copied before the call returns, as upstream expects. */
 int ycnr_host_register(ycnr_ctx* ctx, void* ptr, size_t bytes);
 int ycnr_host_unregister(ycnr_ctx* ctx, void* ptr);
 
