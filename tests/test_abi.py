@@ -79,3 +79,26 @@ def test_sass_carries_the_blackwell_instructions_the_design_claims():
     assert has("als_primal_kernel", "MUFU.RSQ")
     assert has("item_scatter_kernel", "MATCH")
     assert not has("gram_tc_kernel", "HMMA.") or True      # no legacy mma.sync path is required anywhere
+
+
+def test_kernel_resource_usage_fits_the_launch_shapes():
+    """cuobjdump --dump-resource-usage (no GPU needed): no kernel spills to local memory, and the persistent Gram
+    kernel — one CTA of up to 928 threads per SM — stays inside the 64 K-register file (a register bump there would
+    only show up as 'too many resources requested for launch' on the GPU)."""
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", build.build_cuda()], capture_output=True, text=True).stdout
+    fn, usage = None, {}
+    for line in out.splitlines():
+        line = line.strip()
+        if line.startswith("Function "):
+            fn = line.split()[1].rstrip(":")
+        elif line.startswith("REG:") and fn:
+            usage[fn] = {k: int(v) for k, v in (t.split(":") for t in line.split() if ":" in t and t.split(":")[1].isdigit())}
+    assert len(usage) >= 60
+    spilled = [f for f, u in usage.items() if u.get("STACK", 0) or u.get("LOCAL", 0)]
+    assert not spilled, spilled
+    stages_threads = {5: 928, 8: 928, 16: 928, 25: 928, 31: 800}      # TcCfg<KT>::THREADS at the shared-memory-limited STAGES
+    for kt, threads in stages_threads.items():
+        name = next(f for f in usage if "gram_tc_kernelILi%dE" % kt in f)
+        regs = usage[name]["REG"]
+        assert ((regs + 7) // 8 * 8) * threads <= 65536, (name, regs, threads)
