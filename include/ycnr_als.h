@@ -166,6 +166,22 @@ int ycnr_rmse_portion(ycnr_ctx* ctx, const int32_t* rmse_rows, const int32_t* rm
 int ycnr_s_als_build_sub_fixed_facts(ycnr_ctx* ctx, float* sub, const float* fixed, int64_t fixed_rows,
                                      const int32_t* indx, int32_t cols, int32_t k);
 
+/* The upstream export's own arity, (sub, fixed, indx, cols, k) (cpp_utils/cpp_utils.js:15-19) + the row count the
+ * binding knows from the typed array: uses the most recently created live context of the process. */
+int ycnr_s_als_build_sub_fixed_facts_noctx(float* sub, const float* fixed, int64_t fixed_rows, const int32_t* indx,
+                                           int32_t cols, int32_t k);
+
+/* Host-only check of a portion header against the lengths of the arrays that carry it (the typed arrays of the
+ * N-API binding, EmfWorker.js:176-219 reads them unchecked): rows_len words of alsRows/rmseRows, indx_len /
+ * vals_len entries.  Row and column ids are checked by the portion calls themselves (rows on the host, columns
+ * on the device). */
+int ycnr_check_portion(const int32_t* rows, int64_t rows_len, int64_t indx_len, int64_t vals_len);
+/* total_users * factors_count (which = 0) or total_items * factors_count: what attachFactors must be given */
+int ycnr_factor_elems(ycnr_ctx* ctx, int32_t which, int64_t* elems_out);
+/* 'getMemoryUsage' (EmfWorker.js:43,109-113; EmfBase.js:880-934): out[4] = device bytes held by the context,
+ * page-locked host bytes (slots + registered regions), free and total device memory. */
+int ycnr_memory_usage(ycnr_ctx* ctx, int64_t out[4]);
+
 /* ---- bulk path: all portions of a step resident on the device ------------- */
 /* A row set is the concatenation of the portion headers of one step: row r covers
  * indx/vals[row_start[r] .. row_start[r]+row_len[r]).  span = number of entries of
@@ -179,6 +195,11 @@ int ycnr_rowset_destroy(ycnr_ctx* ctx, int32_t rowset);
 /* One half-step over the row set, asynchronous on the context stream; device replicas
  * only (use ycnr_download_factors for the host copy). */
 int ycnr_als_rowset(ycnr_ctx* ctx, int32_t rowset);
+/* Queue the RMSE pass of a row set without waiting for it (a master that knows the next passes — validate and
+ * test with shift 0, EmfLord.js:896-897 — starts them together); ycnr_rmse_rowset then only waits.  The sums of
+ * the last pass are kept per row set together with the sum of the ratings, so a pass with ANOTHER shift over
+ * unchanged factors (EmfLord.js:898) is derived on the host: sum (r-p-d)^2 = sum (r-p)^2 - 2d (sum r - sum p) + n d^2. */
+int ycnr_rmse_rowset_begin(ycnr_ctx* ctx, int32_t rowset, double global_avg_shift);
 /* totals[3] = {rSumDiff2, rCnt, rSum}; portion_sums[n_portions*3] optional. Synchronous. */
 int ycnr_rmse_rowset(ycnr_ctx* ctx, int32_t rowset, double global_avg_shift, double* totals,
                      double* portion_sums);
@@ -247,6 +268,8 @@ int ycnr_debug_read_partials(ycnr_ctx* ctx, float* out, int64_t n_floats);
 /* ---- measurement ------------------------------------------------------------ */
 int ycnr_profile_reset(ycnr_ctx* ctx);
 int ycnr_profile_read(ycnr_ctx* ctx, ycnr_profile* out);   /* synchronises the stream */
+/* YCNR_K_DUAL_FUSED broken down by dual bin (tile-row count 1..24): device ms and rows since the last reset */
+int ycnr_profile_dual_bins(ycnr_ctx* ctx, double ms_out[24], int64_t rows_out[24]);
 
 #ifdef __cplusplus
 }

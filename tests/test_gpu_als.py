@@ -501,7 +501,7 @@ def test_checkpoint_resume_is_bitwise(tmp_path):
     c = EmfMaster(prob["table"], opts)
     c.splitDataForTrain()
     U1, V1, ci = EmfManager(c, str(tmp_path / "ml")).loadCalcResults()
-    assert ci["calcCnt"] == 2 and ci["factorsCount"] == 20      # per-iteration checkpoint + the final save
+    assert ci["calcCnt"] == 1 and ci["factorsCount"] == 20      # one train run (EmfLord.js:904), however many checkpoints
     c.prepareToTrain(U1, V1)
     hc = c.trainIter()
     c.syncFactorsToHost()

@@ -140,11 +140,59 @@ def test_netflix_default_portions_sampled_vs_oracle():
     run_sampled_shape("netflix", 100, n_user=64, n_item=6, n_rmse=24, with_o64=False)
 
 
-@pytest.mark.parametrize("k", [32, 64, 128])
+@pytest.mark.parametrize("k", [32, 64, 128, 192, 256])
 def test_k_sweep_mal_subsample_vs_oracle(k):
-    """BASELINE configs[4] (k sweep) on a MAL-shaped subsample: 120 K users x 12.7 K items, 8.3 M ratings, same
-    power-law row lengths; all three kernel classes (dual, tensor-core / FFMA Gram, k x k solve) at every k."""
+    """BASELINE configs[4] (k sweep 32/64/128/256) on a MAL-shaped subsample: 120 K users x 12.7 K items, 8.3 M
+    ratings, same power-law row lengths; all three kernel classes (dual, tensor-core Gram — one pass up to k = 124,
+    one pass per pair of column blocks above —, k x k solve) at every k."""
     run_sampled_shape("mal", k, n_user=48, n_item=6, n_rmse=12, users=120_000, items=12_700, ratings=8_300_000)
+
+
+@pytest.mark.parametrize("k", [128, 132, 160, 192, 224, 256])
+def test_wide_systems_adversarial_rows_vs_oracle(k):
+    """k > 124 (the reference allocates A for any factorsCount, EmfWorker.js:200-211; its author recommends 300-400
+    for MAL, EmfBase.js:90): dual rows, rows around k, multi-slice rows, both step types, vs O32 and O64."""
+    assert oracle.set_blas(threads=1)
+    rng = np.random.default_rng(200 + k)
+    n_fixed, n_solved = 9000, 48
+    F = rng.normal(0, 0.3, (n_fixed, k)).astype(np.float32)
+    lens = [1, 5, 95, 96, 97, 127, 128, 129, k - 1, k, k + 1, 2 * k + 3, 4095, 4096, 4097, 8999]
+    ids = list(range(2, 2 + 2 * len(lens), 2))
+    cols = [np.sort(rng.choice(n_fixed, n, replace=False)).tolist() for n in lens]
+    vals = [rng.integers(1, 11, n).astype(float).tolist() for n in lens]
+    from tests.helpers import portion_from_rows
+    rows, indx, v = portion_from_rows(ids, cols, vals)
+    S0 = rng.normal(0, 0.1, (n_solved, k)).astype(np.float32)
+    S64 = S0.astype(np.float64)
+    oracle.als_portion(rows, indx, v, F.astype(np.float64), S64, 0.05, use_blas=True)
+    S32 = S0.copy()
+    oracle.als_portion(rows, indx, v, F, S32, 0.05, use_blas=True)
+    for step in (native.BY_USER, native.BY_ITEM):
+        S = S0.copy()
+        if step == native.BY_USER:
+            ctx = native.Context(k, n_solved, n_fixed, 0.05, 0.05, profile=True)
+            ctx.attach_factors(S, F)
+        else:
+            ctx = native.Context(k, n_fixed, n_solved, 0.05, 0.05, profile=True)
+            ctx.attach_factors(F, S)
+        ctx.start_train_step(step)
+        ctx.als_portion(rows, indx, v)
+        ctx.end_train_step()
+        prof = ctx.profile_read()
+        nb = (k + 59) // 60
+        assert prof["gram_tc"]["launches"] == nb * (nb - 1) // 2 and prof["reduce_solve"]["rows"] == len(lens) - 4
+        untouched = np.setdiff1d(np.arange(n_solved), ids)
+        assert (S[untouched] == S0[untouched]).all()
+        assert worst_row_rel(S[ids], S64[ids]) < FACTOR_TOL and worst_row_rel(S[ids], S32[ids]) < FACTOR_TOL
+        assert rel_fro(S[ids], S64[ids]) < 2e-4
+        ctx.close()
+
+
+def test_wide_system_option_errors():
+    for kw, pat in ((dict(factors_count=130), "% 4"), (dict(factors_count=256, gram_path=native.GRAM_FFMA), "tensor-core"),
+                    (dict(factors_count=260), "1..256")):
+        with pytest.raises(RuntimeError, match=pat):
+            native.Context(kw.pop("factors_count"), 10, 10, **kw)
 
 
 @pytest.mark.parametrize("bulk", [False, True])

@@ -129,3 +129,84 @@ def test_launch_plan_classes_cpu():
     q = native.debug_plan(lens, factors_count=7)
     assert list(q["dual"][0]) == [1, 2] and sum(len(b) for b in q["dual"]) == 2
     assert list(q["fused"]) == [6, 11, 5, 4, 10, 3] and list(q["multi"]) == [7, 8]
+
+
+def test_init_first_factor_as_avg_rating_cpu():
+    """als.initFirstFactorAsAvgRating (EmfBase.js:500-511): the first factor of every row that has ratings is its
+    average rating over sets 1,2,3 (EmfLord.getStats, EmfLord.js:67-119); rows without ratings keep the random
+    draw (`avg !== undefined`, not `avg > 0`)."""
+    import numpy as np
+    from you_can_not_recommend_b200 import front_end as fe
+    from you_can_not_recommend_b200.emf_master import EmfMaster
+    # user 2 and item 3 have no ratings at all
+    t = fe.table_from_triples(4, 5, [0, 0, 1, 3, 3, 3], [0, 1, 1, 0, 2, 4], [5, 3, 4, 1, 2, 3])
+    m = EmfMaster(t, {"factorsCount": 4, "als": {"initFirstFactorAsAvgRating": True}})
+    m.splitDataForTrain()
+    m.createSharedFactors()
+    m.initSharedFactorsRandom()
+    plain = EmfMaster(t, {"factorsCount": 4})
+    plain.splitDataForTrain()
+    plain.createSharedFactors()
+    plain.initSharedFactorsRandom()
+    assert np.allclose(m.userFactors[[0, 1, 3], 0], [4.0, 4.0, 2.0])
+    assert np.allclose(m.itemFactors[[0, 1, 2, 4], 0], [3.0, 3.5, 2.0, 3.0])
+    assert m.userFactors[2, 0] == plain.userFactors[2, 0] and m.itemFactors[3, 0] == plain.itemFactors[3, 0]
+    assert (m.userFactors[:, 1:] == plain.userFactors[:, 1:]).all()
+    assert "ratingsAvgPerUser" in m.stats and plain.stats["ratingsAvgPerUser"] is None
+
+
+def test_manager_calc_cnt_once_per_run_cpu(tmp_path):
+    """calcCnt goes up once per train run (EmfLord.js:904) however many per-iteration checkpoints are written,
+    the last checkpoint is not written twice, and only rank 0 touches the directories."""
+    import json
+    import numpy as np
+    from you_can_not_recommend_b200.emf_base import default_options
+    from you_can_not_recommend_b200.emf_manager import EmfManager
+
+    class M:
+        def __init__(self, rank):
+            self.options = default_options()
+            self.options["checkpointEveryIter"] = True
+            self.ctx, self.rank, self.history, self.saves = None, rank, [], 0
+            self.factorsCount, self.totalUsersCount, self.totalItemsCount, self.globalAvgShift = 2, 3, 2, 0.0
+            self.userFactors = np.ones((3, 2), np.float32)
+            self.itemFactors = np.ones((2, 2), np.float32)
+
+        def trainIter(self):
+            self.userFactors += 1
+            self.history.append({})
+
+    m = M(0)
+    mgr = EmfManager(m, str(tmp_path / "a"))
+    orig = mgr.saveCalcResults
+    count = []
+    mgr.saveCalcResults = lambda *a: (count.append(1), orig(*a))[1]
+    mgr.train(3)
+    assert len(count) == 3                                                    # 3 checkpoints, no extra final save
+    ci = json.load(open(tmp_path / "a_factors_ready" / "calc_info.json"))
+    assert ci["calcCnt"] == 1
+    assert np.fromfile(tmp_path / "a_factors_ready" / "user_factors", np.float32)[0] == 4.0
+    mgr.train(1)
+    assert json.load(open(tmp_path / "a_factors_ready" / "calc_info.json"))["calcCnt"] == 2
+    m1 = M(1)
+    EmfManager(m1, str(tmp_path / "b")).train(2)
+    assert not (tmp_path / "b_factors_ready").exists() and not (tmp_path / "b_factors_temp").exists()
+
+
+def test_check_portion_header_against_array_lengths_cpu():
+    """ycnr_check_portion (host only): the header must fit the arrays that carry it — what the N-API binding
+    checks before it hands typed arrays to the portion calls (EmfWorker.js:176-219 reads them unchecked)."""
+    import ctypes as C
+    import numpy as np
+    from you_can_not_recommend_b200 import native
+    L = native.lib()
+    rows = np.asarray([2, 5, 3, 9, 4], np.int32)
+
+    def chk(r, ni, nv):
+        return L.ycnr_check_portion(r.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(len(r)), C.c_int64(ni), C.c_int64(nv))
+    assert chk(rows, 7, 7) == 0 and chk(rows, 8, 9) == 0
+    assert chk(rows, 6, 7) != 0 and b"do not fit the indx/vals" in L.ycnr_last_error()
+    assert chk(rows[:4], 7, 7) != 0 and b"do not fit the rows array" in L.ycnr_last_error()
+    assert chk(np.asarray([-1], np.int32), 0, 0) != 0
+    assert chk(np.asarray([1, 0, -2], np.int32), 5, 5) != 0 and b"negative cols" in L.ycnr_last_error()
+    assert chk(np.asarray([0], np.int32), 0, 0) == 0

@@ -63,6 +63,7 @@ def build_cuda(force=False, verbose=False):
             raise RuntimeError("nvcc not found: the CUDA hot path cannot be built (there is no CPU fallback)")
         cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo"] + NVCC_ARCH + [
             "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE, "-I", CSRC]
+        cmd += os.environ.get("YCNR_NVCC_FLAGS", "").split()       # tuning experiments: -DYCNR_...=n
         if verbose:
             cmd += ["-Xptxas", "-v"]
         cmd += srcs + ["-o", CUDA_LIB, "-lcudart"]

@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(NT) als_primal_kernel(const PrimalArgs a) {
   __shared__ __align__(16) float minv[KT * 16];
   __shared__ __align__(16) float ysm[KP];
 
+  if (rows_poisoned(a.rows)) return;
   const int tid = threadIdx.x;
   const int k = a.k;
   int tI[TPT], tL[TPT];
@@ -388,6 +389,100 @@ __global__ void __launch_bounds__(NT) als_primal_kernel(const PrimalArgs a) {
 }
 
 // ------------------------------------------------------------------------------------
+// Solve of systems wider than one tensor-core pass (k > 124).  The Gram kernel covered the k x k system by one
+// pass per PAIR (a < b) of column blocks (wt tile rows each); pass p left, per slice, the tile partials of the
+// 2 wt x 2 wt "virtual" system [block a | block b] in the usual column-major tile enumeration.  This kernel
+// assembles every tile (I, L) of the full system from the pass that holds it, sums the row's slices in a fixed
+// order, adds the ridge and runs the same register-tile Cholesky.
+// ------------------------------------------------------------------------------------
+struct SolveBlocksArgs {
+  RowsView rows;
+  int k;
+  double lambda;
+  DstList dst;
+  const int32_t* __restrict__ work;            // row index per CTA
+  const int32_t* __restrict__ row_first_item;  // first slice of the row (index into the step's work items)
+  const int32_t* __restrict__ row_n_items;
+  const float* __restrict__ partial;           // [pass][item - item_base][virtual tiles][16]
+  size_t pass_stride;                          // floats between passes
+  int item_base;
+  int nb, wt;                                  // column blocks, tile rows per block
+};
+
+// linear index of tile (Iv, Lv) (Iv == ktv: rhs row) in the column-major enumeration of a ktv-row system
+__device__ __forceinline__ int tile_linear(int Iv, int Lv, int ktv) {
+  return Lv * (ktv + 1) - (Lv * (Lv - 1)) / 2 + (Iv - Lv);
+}
+
+template <int KT, int NT, int TPT>
+__global__ void __launch_bounds__(NT) als_solve_blocks_kernel(const SolveBlocksArgs a) {
+  constexpr int KP = 4 * KT;
+  constexpr int NTRI = KT * (KT + 1) / 2;
+  constexpr int NTILES = NTRI + KT;
+  static_assert(NT * TPT >= NTILES, "not enough threads for the tile set");
+  if (rows_poisoned(a.rows)) return;
+  __shared__ __align__(16) float panel[(KT + 1) * 16];
+  __shared__ __align__(16) float minv[KT * 16];
+  __shared__ __align__(16) float ysm[KP];
+  const int tid = threadIdx.x;
+  const int k = a.k, nb = a.nb, wt = a.wt;
+  const int ktv = 2 * wt, ntv = ktv * (ktv + 1) / 2 + ktv;
+  const int row = a.work[blockIdx.x];
+  const int first = a.row_first_item[blockIdx.x] - a.item_base;
+  const int nit = a.row_n_items[blockIdx.x];
+  const float lam = (float)(a.lambda * (double)a.rows.row_len[row]);
+
+  int tI[TPT], tL[TPT];
+  float acc[TPT][4][4];
+#pragma unroll
+  for (int q = 0; q < TPT; ++q) {
+    const int t = tid + q * NT;
+    if (t < NTILES) tile_coords(t, KT, NTRI, tI[q], tL[q]);
+    else { tI[q] = -1; tL[q] = -1; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[q][i][j] = 0.f;
+    if (tI[q] < 0) continue;
+    const int I = tI[q], L = tL[q];
+    const int sb = L / wt;
+    const int sa = I == KT ? sb : I / wt;
+    if (sb >= nb || sa >= nb) continue;                     // padding tiles beyond the last block: zero
+    int pa, pb;                                             // the pass (pa < pb) that holds the tile
+    if (sa != sb) { pa = sb; pb = sa; }
+    else if (sb + 1 < nb) { pa = sb; pb = sb + 1; }
+    else { pa = sb - 1; pb = sb; }
+    const int pass = pa * nb - (pa * (pa + 1)) / 2 + (pb - pa - 1);
+    const int Lv = L - sb * wt + (sb == pb ? wt : 0);
+    const int Iv = I == KT ? ktv : I - sa * wt + (sa == pb ? wt : 0);
+    const float* in = a.partial + (size_t)pass * a.pass_stride + ((size_t)first * ntv + tile_linear(Iv, Lv, ktv)) * 16;
+    for (int it = 0; it < nit; ++it, in += (size_t)ntv * 16) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(in + 4 * i);
+        acc[q][i][0] += v.x; acc[q][i][1] += v.y; acc[q][i][2] += v.z; acc[q][i][3] += v.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < TPT; ++q) {
+    if (tI[q] >= 0 && tI[q] == tL[q]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (4 * tI[q] + i < k) acc[q][i][i] += lam;
+        else acc[q][i][i] = 1.0f;
+      }
+    }
+  }
+  tile_cholesky_solve<TPT>(acc, tI, tL, KT, panel, minv, ysm);
+  const int rowId = a.rows.row_ids[row];
+  for (int c = tid; c < k; c += NT) {
+    const float x = ysm[c];
+    for (int d = 0; d < a.dst.n; ++d) a.dst.p[d][(size_t)rowId * k + c] = x;
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Dual kernel: rows with n <= 4*MT_MAX ratings, n x n system  G = Y Y^T + lambda*n I.
 // ------------------------------------------------------------------------------------
 struct DualArgs {
@@ -423,6 +518,7 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
   float* vs = ysm + NMAX;                      // NMAX
   float* red = vs + NMAX;                      // K-split partial tiles: [G-1][4][ntl] float4
 
+  if (rows_poisoned(a.rows)) return;
   const int tid = threadIdx.x;
   const int k = a.k, pitch = a.pitch;
   const int K4 = (k + 3) & ~3;
@@ -588,6 +684,155 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
     }
     const float x = (x0 + x1) + (x2 + x3);
     for (int d = 0; d < a.dst.n; ++d) a.dst.p[d][(size_t)rowId * k + c] = x;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Dual kernel, several tiles per thread: the same n x n system, but the CTA is only as wide as
+// ceil(ntl / TPT) threads (rounded to warps).  Every step of the factorisation costs each WARP of the CTA a
+// fixed number of control instructions and two barriers whether or not its lanes hold live tiles, so the
+// thread-per-tile kernel above pays that overhead 11 times per step at mt = 24; with three or four tiles per
+// thread it is paid 3 times and the CTAs are small enough for more systems to be resident per SM.
+// MT is exact (the host bins rows by tile-row count).
+// ------------------------------------------------------------------------------------
+template <int MT, int NT, int TPT>
+__global__ void __launch_bounds__(NT) als_dual_tpt_kernel(const DualArgs a) {
+  constexpr int NMAX = 4 * MT;
+  constexpr int NTRI = MT * (MT + 1) / 2;
+  constexpr int NTL = NTRI + MT;
+  static_assert(NT * TPT >= NTL, "not enough threads for the tile set");
+  if (rows_poisoned(a.rows)) return;
+  extern __shared__ __align__(16) float dsm[];
+  float* Y = dsm;                          // [NMAX][pitch]
+  float* panel = Y + NMAX * a.pitch;       // (MT+1)*16
+  float* minv = panel + (MT + 1) * 16;     // MT x 16
+  float* ysm = minv + MT * 16;             // NMAX
+  float* vs = ysm + NMAX;                  // NMAX
+
+  const int tid = threadIdx.x;
+  const int k = a.k, pitch = a.pitch;
+  const int K4 = (k + 3) & ~3;
+  const int row = a.work[blockIdx.x];
+  const int64_t beg = a.rows.row_start[row];
+  const int n = a.rows.row_len[row];
+  constexpr int mt = MT;
+  constexpr int np = 4 * MT;
+
+  if ((k & 3) == 0) {
+    const int CH = k >> 2;
+    for (int q = tid; q < np * CH; q += NT) {
+      const int r = q / CH, c = q - r * CH;
+      const bool ok = r < n;
+      const int col = ok ? __ldg(a.rows.indx + beg + r) : 0;
+      cp_async16(Y + ((r & 3) * mt + (r >> 2)) * pitch + 4 * c, a.fixed + (size_t)col * k + 4 * c, ok ? 16 : 0);
+    }
+  } else {
+    for (int q = tid; q < np * K4; q += NT) {
+      const int r = q / K4, c = q - r * K4;
+      const bool ok = r < n && c < k;
+      const int col = ok ? __ldg(a.rows.indx + beg + r) : 0;
+      cp_async4(Y + ((r & 3) * mt + (r >> 2)) * pitch + c, a.fixed + (size_t)col * k + (ok ? c : 0), ok ? 4 : 0);
+    }
+  }
+  for (int r = tid; r < np; r += NT) vs[r] = r < n ? __ldg(a.rows.vals + beg + r) : 0.f;
+  cp_async_commit();
+
+  int tI[TPT], tL[TPT];
+#pragma unroll
+  for (int q = 0; q < TPT; ++q) {
+    const int t = tid + q * NT;
+    if (t < NTL) tile_coords(t, mt, NTRI, tI[q], tL[q]);
+    else { tI[q] = -1; tL[q] = -1; }
+  }
+  float acc[TPT][4][4];
+  cp_async_wait<0>();
+  __syncthreads();
+
+  const float lam = (float)(a.lambda * (double)n);
+  const int tstride = mt * pitch;
+#pragma unroll
+  for (int q = 0; q < TPT; ++q) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[q][i][j] = 0.f;
+    if (tI[q] >= 0 && tI[q] < mt) {
+      const float* ya = Y + tI[q] * pitch;
+      const float* yb = Y + tL[q] * pitch;
+      float2 acc2[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
+#pragma unroll 2
+      for (int c = 0; c < K4; c += 4) {
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          av[i] = *reinterpret_cast<const float4*>(ya + i * tstride + c);
+          bv[i] = *reinterpret_cast<const float4*>(yb + i * tstride + c);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 s = acc2[i][j];
+            s = __ffma2_rn(make_float2(av[i].x, av[i].y), make_float2(bv[j].x, bv[j].y), s);
+            s = __ffma2_rn(make_float2(av[i].z, av[i].w), make_float2(bv[j].z, bv[j].w), s);
+            acc2[i][j] = s;
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[q][i][j] = acc2[i][j].x + acc2[i][j].y;
+      if (tI[q] == tL[q]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (4 * tI[q] + i < n) acc[q][i][i] += lam;
+          else acc[q][i][i] = 1.0f;
+        }
+      }
+    } else if (tI[q] == mt) {
+      const float4 v = *reinterpret_cast<const float4*>(vs + 4 * tL[q]);
+      acc[q][0][0] = v.x; acc[q][0][1] = v.y; acc[q][0][2] = v.z; acc[q][0][3] = v.w;
+    }
+  }
+  __syncthreads();   // vs is rewritten below only after the solve; Y stays
+  tile_cholesky_solve<TPT>(acc, tI, tL, mt, panel, minv, ysm);
+
+  const int rowId = a.rows.row_ids[row];
+  for (int p = tid; p < np; p += NT) vs[(p & 3) * mt + (p >> 2)] = ysm[p];   // z in slot order (pad rows: z = 0)
+  __syncthreads();
+  if ((k & 3) == 0) {
+    // one float4 of the solution per thread: np LDS.128 + broadcast LDS of z, 4 FMA each
+    for (int c4 = tid; c4 < (k >> 2); c4 += NT) {
+      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+      const float* yc = Y + 4 * c4;
+#pragma unroll 2
+      for (int s2 = 0; s2 < np; s2 += 2) {
+        const float4 y0 = *reinterpret_cast<const float4*>(yc + (s2 + 0) * pitch);
+        const float4 y1 = *reinterpret_cast<const float4*>(yc + (s2 + 1) * pitch);
+        const float z0 = vs[s2], z1 = vs[s2 + 1];
+        x0.x = fmaf(y0.x, z0, x0.x); x0.y = fmaf(y0.y, z0, x0.y); x0.z = fmaf(y0.z, z0, x0.z); x0.w = fmaf(y0.w, z0, x0.w);
+        x1.x = fmaf(y1.x, z1, x1.x); x1.y = fmaf(y1.y, z1, x1.y); x1.z = fmaf(y1.z, z1, x1.z); x1.w = fmaf(y1.w, z1, x1.w);
+      }
+      const float4 x = make_float4(x0.x + x1.x, x0.y + x1.y, x0.z + x1.z, x0.w + x1.w);
+      for (int d = 0; d < a.dst.n; ++d) *reinterpret_cast<float4*>(a.dst.p[d] + (size_t)rowId * k + 4 * c4) = x;
+    }
+  } else {
+    for (int c = tid; c < k; c += NT) {
+      float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+      const float* yc = Y + c;
+      for (int s2 = 0; s2 < np; s2 += 4) {
+        x0 = fmaf(yc[(s2 + 0) * pitch], vs[s2 + 0], x0);
+        x1 = fmaf(yc[(s2 + 1) * pitch], vs[s2 + 1], x1);
+        x2 = fmaf(yc[(s2 + 2) * pitch], vs[s2 + 2], x2);
+        x3 = fmaf(yc[(s2 + 3) * pitch], vs[s2 + 3], x3);
+      }
+      const float x = (x0 + x1) + (x2 + x3);
+      for (int d = 0; d < a.dst.n; ++d) a.dst.p[d][(size_t)rowId * k + c] = x;
+    }
   }
 }
 

@@ -20,7 +20,14 @@ struct RowsView {
   const int32_t* __restrict__ row_len;
   const int32_t* __restrict__ indx;
   const float* __restrict__ vals;
+  // per-portion path only: device flag raised by validate_cols_kernel when a column id of a queued portion
+  // lies outside the fixed matrix; the compute kernels of the step then leave without touching memory
+  const int32_t* __restrict__ guard;
 };
+
+__device__ __forceinline__ bool rows_poisoned(const RowsView& r) {
+  return r.guard != nullptr && *reinterpret_cast<const volatile int32_t*>(r.guard) != 0;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -50,4 +57,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// Column ids of a portion in the upstream wire format are trusted by the reference worker (EmfWorker.js:217-228
+// indexes the fixed matrix with them unchecked and degrades to NaN); here an id outside [0, limit) would be an
+// out-of-bounds gather, so the per-portion path checks them on the device right after the upload.
+__global__ void __launch_bounds__(256) validate_cols_kernel(const int32_t* __restrict__ indx, int64_t n, int32_t limit,
+                                                            int32_t* __restrict__ flag) {
+  bool bad = false;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+    bad |= (uint32_t)__ldg(indx + e) >= (uint32_t)limit;
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }

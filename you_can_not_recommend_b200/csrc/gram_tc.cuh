@@ -104,6 +104,11 @@ struct GramTcArgs {
   int split_cols;
   float* __restrict__ partial;   // [items][tiles][16]
   int prefetch;                  // 1: the fixed matrix does not fit L2, loaders prefetch far-ahead rows into it
+  // Column map of the virtual system the kernel builds: its first chunks_a 16-byte chunks are columns
+  // [col_a, col_a + 4 chunks_a) of the gathered rows, the remaining ones start at col_b; columns >= k read as zero.
+  // One pass over all columns (k <= 124): col_a = 0, chunks_a = KT.  Systems with k > 124 are covered by one
+  // pass per PAIR of column blocks (blocks of w <= 60 columns, 2 w + 4 <= 128), see launch_primal_blocks.
+  int col_a, col_b, chunks_a;
   uint32_t variant;              // diagnostics: 16 = splitters also overwrite the H columns with explicitly masked values
 };
 
@@ -205,6 +210,7 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(Cfg::N >> 3) << 17) | ((128u >> 4) << 24);
 
+  if (rows_poisoned(a.rows)) return;   // uniform for the whole grid: nothing has been allocated yet
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   // carve: [stages][STAGE_BYTES] | Xs[NC][XP] | barriers | tmem base
   // SWIZZLE_128B atoms are addressed by absolute shared-memory bits [7,10): align the ring to 1024 B
@@ -281,8 +287,9 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
         }
         vm = __ballot_sync(0xffffffffu, ok);
       };
-      const float* src_lane = a.fixed + 4 * lane;
-      const bool lane_ok = lane < KT && 4 * lane < k;
+      const int src_col = lane < a.chunks_a ? a.col_a + 4 * lane : a.col_b + 4 * (lane - a.chunks_a);
+      const float* src_lane = a.fixed + src_col;
+      const bool lane_ok = lane < KT && src_col < k;
       const uint32_t val_off = tc_chunk_offset(lane & (HR - 1), 4 * KT);
       auto issue = [&](uint32_t use, int col, uint32_t vm, int64_t e0) {
         mbar_wait(empty0 + 8 * s_own, (use & 1u) ^ 1u);
@@ -314,11 +321,19 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
             col = __ldg(a.rows.indx + x.seg_beg + (int64_t)x.st * kTcStageRows + rr);
         }
       };
+      const bool one_range = a.chunks_a >= KT;
       auto prefetch_rows = [&](int col) {
         if (col >= 0) {
-          const char* p = reinterpret_cast<const char*>(a.fixed + (size_t)col * k) + (lane >> 4) * 128;
-          if ((lane >> 4) * 128 < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
-          if ((lane >> 4) * 128 + 256 < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p + 256));
+          if (one_range) {
+            const char* p = reinterpret_cast<const char*>(a.fixed + (size_t)col * k) + (lane >> 4) * 128;
+            if ((lane >> 4) * 128 < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+            if ((lane >> 4) * 128 + 256 < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p + 256));
+          } else {   // two column ranges of at most 240 bytes: two lines each (the lines they start in and the next)
+            const char* row = reinterpret_cast<const char*>(a.fixed + (size_t)col * k);
+            const int oa = a.col_a * 4 + (lane >> 4) * 128, ob = a.col_b * 4 + (lane >> 4) * 128;
+            if (oa < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + oa));
+            if (ob < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + ob));
+          }
         }
       };
       int pcol = -1;

@@ -18,7 +18,7 @@ namespace ycnr {
 
 constexpr int kScanThreads = 256;
 constexpr int kScanRowsPerBlock = 2048;
-constexpr int kItemChunk = 32768;        // table entries per block of the by-item counting sort
+constexpr int kItemChunk = 32768;        // table entries per block of the by-item counting sort (grows with the catalog, see ycnr_rowset_from_table)
 
 __device__ __forceinline__ bool in_set(int8_t dt, uint32_t mask) { return (mask >> (uint32_t)(dt & 31)) & 1u; }
 
@@ -129,10 +129,10 @@ __global__ void __launch_bounds__(256) fill_by_user_kernel(const int64_t* __rest
 // ---- the fetch "by item": stable counting sort of the table by item id ----------------------------------
 // counts[b][i] = entries of item i (in the set) inside table chunk b
 __global__ void __launch_bounds__(256) item_hist_kernel(const int32_t* __restrict__ item, const int8_t* __restrict__ dt,
-                                                        uint32_t mask, int64_t nnz, int items,
+                                                        uint32_t mask, int64_t nnz, int items, int64_t chunk,
                                                         int32_t* __restrict__ counts) {
-  const int64_t e0 = (int64_t)blockIdx.x * kItemChunk;
-  const int64_t e1 = min(nnz, e0 + (int64_t)kItemChunk);
+  const int64_t e0 = (int64_t)blockIdx.x * chunk;
+  const int64_t e1 = min(nnz, e0 + chunk);
   int32_t* mine = counts + (size_t)blockIdx.x * items;
   for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x)
     if (in_set(dt[e], mask)) atomicAdd(mine + item[e], 1);
@@ -157,12 +157,12 @@ __global__ void __launch_bounds__(256) item_chunk_offsets_kernel(int32_t* __rest
 // row keeps the table's user order, exactly as the host front end produces it.
 __global__ void __launch_bounds__(32) item_scatter_kernel(const int32_t* __restrict__ item, const float* __restrict__ rating,
                                                           const int8_t* __restrict__ dt, const int32_t* __restrict__ elem_user,
-                                                          uint32_t mask, int64_t nnz, int items,
+                                                          uint32_t mask, int64_t nnz, int items, int64_t chunk,
                                                           int32_t* __restrict__ cursors, const int64_t* __restrict__ item_ptr,
                                                           int32_t* __restrict__ idx, float* __restrict__ vals) {
   const int lane = threadIdx.x;
-  const int64_t c0 = (int64_t)blockIdx.x * kItemChunk;
-  const int64_t c1 = min(nnz, c0 + (int64_t)kItemChunk);
+  const int64_t c0 = (int64_t)blockIdx.x * chunk;
+  const int64_t c1 = min(nnz, c0 + chunk);
   int32_t* cur = cursors + (size_t)blockIdx.x * items;
   for (int64_t e0 = c0; e0 < c1; e0 += 32) {
     const int64_t e = e0 + lane;

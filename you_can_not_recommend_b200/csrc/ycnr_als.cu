@@ -27,6 +27,7 @@
 namespace {
 
 thread_local char g_err[1024] = "";
+ycnr_ctx* g_default_ctx = nullptr;   // the most recently created live context (handle-less cpp_utils export)
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -225,7 +226,7 @@ PlanCfg derive_plan_cfg(const ycnr_options& o, bool* use_tc_out) {
   if (cfg.dual_max > cfg.split_cols) cfg.dual_max = cfg.split_cols;
   // AUTO: tensor cores whenever the rhs column fits the M = 128 accumulator and rows are 16-byte aligned
   const bool use_tc = o.gram_path == YCNR_GRAM_TC3XTF32 ||
-                      (o.gram_path == YCNR_GRAM_AUTO && (k & 3) == 0 && k <= 124 && k >= 16);
+                      (o.gram_path == YCNR_GRAM_AUTO && (k & 3) == 0 && k <= 256 && k >= 16);
   cfg.fused_max = use_tc ? (o.tc_min_cols > 0 ? o.tc_min_cols - 1 : 0) : cfg.split_cols;
   if (use_tc_out) *use_tc_out = use_tc;
   return cfg;
@@ -244,6 +245,14 @@ struct RowSet {
   RowsView view{};
   const int32_t* d_portion_first = nullptr;
   DevPlan dplan;
+  // RMSE sets: per-portion sums {rSumDiff2, rCnt, rSum, sum of ratings} of the last pass, its shift and the
+  // versions of the two factor matrices it saw.  While the factors have not changed, a pass with another shift
+  // is derived on the host (the third pass of an iteration, EmfLord.js:898, costs nothing).
+  double* h_sums = nullptr;          // page-locked [P][4]
+  cudaEvent_t sums_ready = nullptr;
+  bool pending = false, cached = false;
+  double cache_shift = 0.0;
+  uint64_t cache_ver[2] = {0, 0};
 };
 
 struct Slot {  // staging for the per-portion path
@@ -259,6 +268,7 @@ constexpr int kSlots = 4;
 struct ProfRec {
   int cls;
   cudaEvent_t a, b;
+  int sub;   // dual bin (tile-row count - 1) or -1
 };
 
 }  // namespace
@@ -270,6 +280,7 @@ struct ycnr_ctx {
   int split_cols = 0;
   int fused_max = 0;       // rows longer than this go through the partial (+reduce) kernels
   bool use_tc = false;     // tcgen05 3xTF32 Gram for the partial kernels
+  bool tc_tested = false;  // tc_self_test ran on this context's device
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D of portion inputs, overlaps the previous portion's kernels
@@ -290,6 +301,7 @@ struct ycnr_ctx {
   bool h_registered[2] = {false, false};
   bool device_current[2] = {false, false};
   int64_t fac_rows[2] = {0, 0};
+  uint64_t fac_version[2] = {1, 1};   // bumped whenever a replica may have changed (cached RMSE sums go stale)
   std::vector<void*> peers[2];
   std::vector<RowSet> rowsets;
   // device-resident ratings table (ycnr_table_upload): user_ptr i64[users+1] | item i32 | rating f32 | dt i8 | elem_user i32
@@ -306,6 +318,10 @@ struct ycnr_ctx {
   DevBuf ingest_tmp;
   DevBuf partial;      // split-row tile partials
   DevBuf gather_tmp;   // ycnr_s_als_build_sub_fixed_facts
+  // per-portion path: column ids are checked on the device (validate_cols_kernel); a raised flag makes the
+  // compute kernels of the step leave early and the step end with an error
+  int32_t* d_bad = nullptr;
+  int32_t* h_bad = nullptr;   // page-locked
   Slot slots[kSlots];
   int next_slot = 0;
   // per-portion step state
@@ -327,6 +343,8 @@ struct ycnr_ctx {
   std::vector<ProfRec> prof_open;
   std::vector<cudaEvent_t> ev_pool;
   ycnr_profile prof{};
+  double dual_bin_ms[kDualBins] = {0};
+  int64_t dual_bin_rows[kDualBins] = {0};
 };
 
 namespace {
@@ -363,8 +381,10 @@ struct ProfScope {
   int cls;
   cudaStream_t st;
   cudaEvent_t a = nullptr, b = nullptr;
-  ProfScope(ycnr_ctx* ctx, int cls_, int64_t rows, int64_t ratings, cudaStream_t stream = nullptr)
-      : c(ctx), cls(cls_), st(stream ? stream : ctx->stream) {
+  int sub = -1;
+  ProfScope(ycnr_ctx* ctx, int cls_, int64_t rows, int64_t ratings, cudaStream_t stream = nullptr, int sub_ = -1)
+      : c(ctx), cls(cls_), st(stream ? stream : ctx->stream), sub(sub_) {
+    if (sub >= 0) c->dual_bin_rows[sub] += rows;
     c->prof.launches[cls]++;
     c->prof.rows[cls] += rows;
     c->prof.ratings[cls] += ratings;
@@ -383,17 +403,94 @@ struct ProfScope {
   ~ProfScope() {
     if (!a) return;
     cudaEventRecord(b, st);
-    c->prof_open.push_back({cls, a, b});
+    c->prof_open.push_back({cls, a, b, sub});
   }
 };
 
 // ---- kernel dispatch -----------------------------------------------------------------
+// gram_tc_kernel feeds the RAW fp32 bits of the gathered rows as the "head" operand and relies on kind::tf32
+// ignoring the low 13 mantissa bits (the PTX text only says the operand "is" tf32).  Once per context: one
+// 64-rating slice with full-mantissa values through the kernel as it is and with explicitly masked heads
+// (variant 16); if the partials differ by a single bit the context keeps the explicit masking on.
 template <int KT>
-int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int item_from, int n_items, int64_t ratings) {
+int tc_self_test(ycnr_ctx* c) {
+  using namespace ycnr;
+  constexpr int NTILES = KT * (KT + 1) / 2 + KT;
+  constexpr int NR = 64;
+  const int k = c->k;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_fix = 0, o_idx = al((size_t)NR * k * 4), o_val = al(o_idx + NR * 4), o_rs = al(o_val + NR * 4);
+  const size_t o_ri = al(o_rs + 8), o_rl = al(o_ri + 4), o_ir = al(o_rl + 4), o_io = al(o_ir + 4);
+  const size_t o_p0 = al(o_io + 4), o_p1 = al(o_p0 + (size_t)NTILES * 64), total = al(o_p1 + (size_t)NTILES * 64);
+  std::vector<char> h(o_p0, 0);
+  float* fx = (float*)(h.data() + o_fix);
+  uint32_t lcg = 12345u;
+  for (int i = 0; i < NR * k; ++i) {
+    lcg = lcg * 1664525u + 1013904223u;
+    fx[i] = ((int)(lcg >> 8) - (1 << 23)) * (1.0f / (1 << 23)) * 0.7f;     // all 24 mantissa bits in use
+  }
+  for (int i = 0; i < NR; ++i) {
+    ((int32_t*)(h.data() + o_idx))[i] = i;
+    ((float*)(h.data() + o_val))[i] = (float)(1 + i % 10);
+  }
+  *(int64_t*)(h.data() + o_rs) = 0;
+  *(int32_t*)(h.data() + o_ri) = 0;
+  *(int32_t*)(h.data() + o_rl) = NR;
+  *(int32_t*)(h.data() + o_ir) = 0;
+  *(int32_t*)(h.data() + o_io) = 0;
+  DevBuf buf;
+  OK(buf.ensure(total));
+  char* d = (char*)buf.p;
+  CU(cudaMemcpyAsync(d, h.data(), o_p0, cudaMemcpyHostToDevice, c->stream));
+  GramTcArgs t{};
+  t.rows.row_start = (const int64_t*)(d + o_rs);
+  t.rows.row_ids = (const int32_t*)(d + o_ri);
+  t.rows.row_len = (const int32_t*)(d + o_rl);
+  t.rows.indx = (const int32_t*)(d + o_idx);
+  t.rows.vals = (const float*)(d + o_val);
+  t.fixed = (const float*)(d + o_fix);
+  t.k = k;
+  t.item_row = (const int32_t*)(d + o_ir);
+  t.item_off = (const int32_t*)(d + o_io);
+  t.n_items = 1;
+  t.split_cols = 4096;
+  t.chunks_a = 1 << 20;
+  const size_t smem = gram_tc_smem_bytes<KT>();
+  OK(ensure_dynamic_smem(c, reinterpret_cast<const void*>(&gram_tc_kernel<KT>), smem));
+  for (int v = 0; v < 2; ++v) {
+    t.partial = (float*)(d + (v ? o_p1 : o_p0));
+    t.variant = v ? 16u : 0u;
+    gram_tc_kernel<KT><<<1, TcCfg<KT>::THREADS, smem, c->stream>>>(t);
+    CU(cudaGetLastError());
+  }
+  c->prof.total_launches += 2;
+  std::vector<uint32_t> out((size_t)NTILES * 32);
+  CU(cudaMemcpyAsync(out.data(), d + o_p0, (size_t)NTILES * 64, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(out.data() + (size_t)NTILES * 16, d + o_p1, (size_t)NTILES * 64, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  buf.release();
+  if (memcmp(out.data(), out.data() + (size_t)NTILES * 16, (size_t)NTILES * 64) != 0) {
+    c->opts.tc_variant |= 16;
+    fprintf(stderr, "[ycnr] kind::tf32 does not truncate raw fp32 operands on this device: explicit head masking enabled\n");
+  }
+  return 0;
+}
+
+struct TcColMap {
+  int col_a = 0, col_b = 0, chunks_a = 1 << 20;   // default: one pass over columns [0, k)
+};
+
+template <int KT>
+int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int item_from, int n_items, int64_t ratings,
+                   float* partial_base = nullptr, TcColMap cm = TcColMap()) {
   using namespace ycnr;
   if constexpr (4 * KT + 4 > 128) {
     return fail("tcgen05 Gram path supports factorsCount <= 124");
   } else {
+    if (!c->tc_tested) {
+      c->tc_tested = true;
+      OK(tc_self_test<KT>(c));
+    }
     GramTcArgs t{};
     t.rows = pa.rows;
     t.fixed = pa.fixed;
@@ -404,7 +501,10 @@ int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int item_from, int n
     t.item_order = (item_from == 0 && n_items == pa.n_items_total) ? pa.item_order : nullptr;   // chunked launches: natural order
     t.n_items = n_items;
     t.split_cols = pa.split_cols;
-    t.partial = pa.partial + (size_t)item_from * NTILES * 16;
+    t.partial = partial_base ? partial_base : pa.partial + (size_t)item_from * NTILES * 16;
+    t.col_a = cm.col_a;
+    t.col_b = cm.col_b;
+    t.chunks_a = cm.chunks_a;
     t.variant = (uint32_t)c->opts.tc_variant;
     t.prefetch = pa.fixed_bytes > ((size_t)48 << 20) ? 1 : 0;
     const size_t smem = gram_tc_smem_bytes<KT>();
@@ -475,15 +575,103 @@ int launch_primal_kt(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p
   return 0;
 }
 
+// ---- k > 124: one tensor-core pass per pair of column blocks ----------------------------------------
+// The tcgen05 Gram holds a system of at most 124 columns (+ the rhs) in its M = 128 accumulator.  Wider systems
+// are cut into nb blocks of w <= 60 columns; the pass for the pair (a < b) gathers only the columns of the two
+// blocks and builds the Gram of the 2 w-column system [a | b] with the kernel as it is — its diagonal quarters
+// are blocks (a,a) and (b,b) of the full matrix, the off-diagonal quarter is block (b,a), its rhs row holds
+// b_a and b_b.  nb (nb - 1) / 2 passes; als_solve_blocks_kernel picks every tile from the pass that holds it.
+struct BlockCfg {
+  int nb, w;
+};
+BlockCfg block_cfg(int k) {
+  const int nb = (k + 59) / 60;
+  for (int w : {44, 52, 60})
+    if (nb * w >= k) return {nb, w};
+  return {nb, 60};
+}
+constexpr size_t kMaxBlockPartialBytes = (size_t)12 << 30;
+
+template <int KT, int NT, int TPT>
+int launch_solve_blocks(ycnr_ctx* c, const ycnr::SolveBlocksArgs& a, int rows) {
+  using namespace ycnr;
+  ProfScope ps(c, YCNR_K_REDUCE_SOLVE, rows, 0);
+  als_solve_blocks_kernel<KT, NT, TPT><<<rows, NT, 0, c->stream>>>(a);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int KTV>
+int launch_primal_blocks(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p, const int32_t* plan_base,
+                         BlockCfg bc) {
+  using namespace ycnr;
+  if (p.n_items <= 0) return 0;
+  constexpr int NTV = KTV * (KTV + 1) / 2 + KTV;
+  const int n_pass = bc.nb * (bc.nb - 1) / 2;
+  int max_items = 0;
+  for (int ch = 0; ch < p.n_chunks; ++ch) max_items = std::max(max_items, p.chunk_item[ch + 1] - p.chunk_item[ch]);
+  const size_t pass_stride = (size_t)max_items * NTV * 16;
+  const size_t bytes = pass_stride * n_pass * sizeof(float);
+  if (bytes > kMaxBlockPartialBytes + (kMaxBlockPartialBytes >> 1))
+    return fail("factorsCount %d: %zu bytes of tile partials for %d rows in one group (internal chunking limit)", c->k, bytes, p.n_multi);
+  OK(c->partial.ensure(bytes));
+  PrimalArgs a = base;
+  a.item_row = plan_base + p.off_item_row;
+  a.item_off = plan_base + p.off_item_off;
+  a.item_order = nullptr;
+  a.n_items_total = p.n_items;
+  a.partial = (float*)c->partial.p;
+  for (int ch = 0; ch < p.n_chunks; ++ch) {
+    const int i0 = p.chunk_item[ch], i1 = p.chunk_item[ch + 1];
+    const int m0 = p.chunk_row[ch], m1 = p.chunk_row[ch + 1];
+    if (i1 <= i0 || m1 <= m0) continue;
+    int pass = 0;
+    for (int ba = 0; ba < bc.nb; ++ba)
+      for (int bb = ba + 1; bb < bc.nb; ++bb, ++pass) {
+        TcColMap cm;
+        cm.col_a = ba * bc.w;
+        cm.col_b = bb * bc.w;
+        cm.chunks_a = bc.w / 4;
+        OK((launch_gram_tc<KTV>(c, a, i0, i1 - i0, p.chunk_ratings[ch], (float*)c->partial.p + pass * pass_stride, cm)));
+      }
+    SolveBlocksArgs sa{};
+    sa.rows = base.rows;
+    sa.k = c->k;
+    sa.lambda = base.lambda;
+    sa.dst = base.dst;
+    sa.work = plan_base + p.off_multi + m0;
+    sa.row_first_item = plan_base + p.off_multi_first + m0;
+    sa.row_n_items = plan_base + p.off_multi_n + m0;
+    sa.partial = (const float*)c->partial.p;
+    sa.pass_stride = pass_stride;
+    sa.item_base = i0;
+    sa.nb = bc.nb;
+    sa.wt = bc.w / 4;
+    const int kt = (c->k + 3) / 4;
+    if (kt <= 32) OK((launch_solve_blocks<32, 192, 3>(c, sa, m1 - m0)));
+    else if (kt <= 40) OK((launch_solve_blocks<40, 288, 3>(c, sa, m1 - m0)));
+    else if (kt <= 48) OK((launch_solve_blocks<48, 320, 4>(c, sa, m1 - m0)));
+    else if (kt <= 56) OK((launch_solve_blocks<56, 416, 4>(c, sa, m1 - m0)));
+    else OK((launch_solve_blocks<64, 480, 5>(c, sa, m1 - m0)));
+  }
+  return 0;
+}
+
 int launch_primal(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p, const int32_t* plan_base) {
   const int k = c->k;
+  if (c->use_tc && k > 124) {
+    const BlockCfg bc = block_cfg(k);
+    if (bc.w == 44) return launch_primal_blocks<22>(c, base, p, plan_base, bc);
+    if (bc.w == 52) return launch_primal_blocks<26>(c, base, p, plan_base, bc);
+    return launch_primal_blocks<30>(c, base, p, plan_base, bc);
+  }
   if (k <= 20) return launch_primal_kt<5, 32>(c, base, p, plan_base);
   if (k <= 32) return launch_primal_kt<8, 64>(c, base, p, plan_base);
   if (k <= 64) return launch_primal_kt<16, 160>(c, base, p, plan_base);
   if (k <= 100) return launch_primal_kt<25, 352>(c, base, p, plan_base);
   if (k <= 124) return launch_primal_kt<31, 544>(c, base, p, plan_base);  // largest KT whose rhs column fits M = 128
   if (k <= 128) return launch_primal_kt<32, 576>(c, base, p, plan_base);
-  return fail("factorsCount %d > 128 is not supported by this build", k);
+  return fail("factorsCount %d > 128 needs the tensor-core Gram (factorsCount %% 4 == 0, gramPath auto or tc)", k);
 }
 
 // threads per CTA for systems of mt tile rows: room for a 2..8-way K-split of the Gram sweep while
@@ -508,10 +696,44 @@ int launch_dual_bin(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t 
   for (int mt = 1; mt <= MT_MAX; ++mt) red = std::max(red, dual_red_floats(mt, NT));
   const size_t smem = ((size_t)4 * MT_MAX * a.pitch + (MT_MAX + 1) * 16 + 16 * MT_MAX + 8 * MT_MAX + red) * sizeof(float);
   if (smem > 48 * 1024) OK(ensure_dynamic_smem(c, reinterpret_cast<const void*>(&als_dual_kernel<MT_MAX, NT>), smem));
-  ProfScope ps(c, YCNR_K_DUAL_FUSED, count, ratings, st);
+  ProfScope ps(c, YCNR_K_DUAL_FUSED, count, ratings, st, MT_MAX - 1);
   als_dual_kernel<MT_MAX, NT><<<count, NT, smem, st>>>(a);
   CU(cudaGetLastError());
   return 0;
+}
+
+// Bins of mt >= YCNR_DUAL2_MIN_MT tile rows run the several-tiles-per-thread kernel: CTA width = the tile set
+// divided by YCNR_DUAL_TPT, rounded up to whole warps.
+#ifndef YCNR_DUAL_TPT
+#define YCNR_DUAL_TPT 3
+#endif
+#ifndef YCNR_DUAL2_MIN_MT
+#define YCNR_DUAL2_MIN_MT 5   // measured on B200 (MAL, k = 100): the K-split kernel only wins for mt <= 4
+#endif
+constexpr int dual2_nt(int mt) { return ((ycnr::dual_ntl(mt) + YCNR_DUAL_TPT - 1) / YCNR_DUAL_TPT + 31) & ~31; }
+constexpr int dual2_tpt(int mt) { return (ycnr::dual_ntl(mt) + dual2_nt(mt) - 1) / dual2_nt(mt); }
+
+template <int MT>
+int launch_dual_bin2(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t ratings, const int32_t* work,
+                     cudaStream_t st) {
+  using namespace ycnr;
+  if (count <= 0) return 0;
+  constexpr int NT = dual2_nt(MT), TPT = dual2_tpt(MT);
+  DualArgs a = base;
+  a.work = work;
+  const size_t smem = ((size_t)4 * MT * a.pitch + (MT + 1) * 16 + 16 * MT + 8 * MT) * sizeof(float);
+  if (smem > 48 * 1024) OK(ensure_dynamic_smem(c, reinterpret_cast<const void*>(&als_dual_tpt_kernel<MT, NT, TPT>), smem));
+  ProfScope ps(c, YCNR_K_DUAL_FUSED, count, ratings, st, MT - 1);
+  als_dual_tpt_kernel<MT, NT, TPT><<<count, NT, smem, st>>>(a);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int MT>
+int launch_dual_bin_any(ycnr_ctx* c, const ycnr::DualArgs& d, int count, int64_t ratings, const int32_t* work,
+                        cudaStream_t st) {
+  if constexpr (MT >= YCNR_DUAL2_MIN_MT) return launch_dual_bin2<MT>(c, d, count, ratings, work, st);
+  else return launch_dual_bin<MT, dual_nt(MT)>(c, d, count, ratings, work, st);
 }
 
 template <int... B>
@@ -519,8 +741,8 @@ int launch_dual_bins(ycnr_ctx* c, const ycnr::DualArgs& d, const DevPlan& p, con
                      std::integer_sequence<int, B...>) {
   int rc = 0;
   ((rc = rc ? rc
-            : launch_dual_bin<B + 1, dual_nt(B + 1)>(c, d, p.n_dual[B], p.ratings_dual[B], plan_base + p.off_dual[B],
-                                                     spread ? c->bin_stream[B % ycnr_ctx::kBinStreams] : c->stream)),
+            : launch_dual_bin_any<B + 1>(c, d, p.n_dual[B], p.ratings_dual[B], plan_base + p.off_dual[B],
+                                         spread ? c->bin_stream[B % ycnr_ctx::kBinStreams] : c->stream)),
    ...);
   return rc;
 }
@@ -573,6 +795,7 @@ int run_als(ycnr_ctx* c, int step_type, const RowsView& view, const DevPlan& p, 
     c->aux_pending = false;
   }
   c->device_current[solved] = true;
+  c->fac_version[solved]++;
   return 0;
 }
 
@@ -589,8 +812,11 @@ int run_rmse(ycnr_ctx* c, const RowsView& view, int n_rows, int64_t nnz, double 
   a.row_sums = d_row_sums;
   {
     ProfScope ps(c, YCNR_K_RMSE_ROWS, n_rows, nnz);
-    const int warps_per_cta = 8;
-    ycnr::rmse_rows_kernel<<<(n_rows + warps_per_cta - 1) / warps_per_cta, 256, 0, c->stream>>>(a);
+    const int rows_per_cta = 32;   // one 8-lane group per row
+    const int grid = (n_rows + rows_per_cta - 1) / rows_per_cta;
+    if ((c->k & 3) == 0 && c->k <= 128) ycnr::rmse_rows_kernel<4><<<grid, 256, 0, c->stream>>>(a);
+    else if ((c->k & 3) == 0 && c->k <= 256) ycnr::rmse_rows_kernel<8><<<grid, 256, 0, c->stream>>>(a);
+    else ycnr::rmse_rows_kernel<0><<<grid, 256, 0, c->stream>>>(a);
   }
   if (d_chunk_sums && n_portions == 1 && n_rows > 2 * ycnr::kRmseChunkRows) {
     // one big portion (per-portion path): two-level fixed-order reduction instead of a single CTA
@@ -615,6 +841,7 @@ int ensure_fixed_current(ycnr_ctx* c, int which) {
   CU(cudaMemcpyAsync(c->d_fac[which], c->h_fac[which], (size_t)c->fac_rows[which] * c->k * sizeof(float),
                      cudaMemcpyHostToDevice, c->stream));
   c->device_current[which] = true;
+  c->fac_version[which]++;
   return 0;
 }
 
@@ -626,10 +853,39 @@ struct StagedPortion {
   int n_rows = 0;
   int64_t ratings = 0;
   int32_t first_row = -1, last_row = -1;
-  double* d_sums = nullptr;        // rmse scratch: row_sums[R][2] | portion_sums[3]
+  double* d_sums = nullptr;        // rmse scratch: row_sums[R][3] | portion_sums[4] | chunk sums
   const int32_t* d_pfirst = nullptr;
   Slot* slot = nullptr;
 };
+
+// The upstream worker trusts the header (EmfWorker.js:176-219); here a stale or corrupt one would turn into
+// out-of-bounds device writes (also into every NVLink peer replica), so row ids are checked against the solved
+// matrix and must ascend strictly (the master emits them in id order, EmfMaster.js:582-609).
+int check_header(const int32_t* rows, int R, int64_t lim_rows, int64_t* ratings_out) {
+  int64_t off = 0;
+  int64_t prev = -1;
+  for (int r = 0; r < R; ++r) {
+    const int64_t id = rows[1 + 2 * (size_t)r];
+    const int n = rows[2 + 2 * (size_t)r];
+    if (n < 0) return fail("portion header: negative cols in row %d", r);
+    if (id < 0 || id >= lim_rows) return fail("portion header: row id %lld outside the factor matrix (0..%lld)", (long long)id, (long long)lim_rows - 1);
+    if (id <= prev) return fail("portion header: row ids must ascend strictly (row %d: %lld after %lld)", r, (long long)id, (long long)prev);
+    prev = id;
+    off += n;
+  }
+  *ratings_out = off;
+  return 0;
+}
+
+int launch_validate_cols(ycnr_ctx* c, const int32_t* d_indx, int64_t n, int64_t lim_cols) {
+  if (n <= 0) return 0;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->num_sms * 8);
+  validate_cols_kernel<<<grid, 256, 0, c->stream>>>(d_indx, n, (int32_t)lim_cols, c->d_bad);
+  CU(cudaGetLastError());
+  c->prof.launches[YCNR_K_GATHER] += 1;
+  c->prof.total_launches += 1;
+  return 0;
+}
 
 int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals, StagedPortion& s) {
   const int R = rows[0];
@@ -637,11 +893,8 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
   s.n_rows = R;
   const int32_t* hdr_len = rows + 2;   // (rowId, n) pairs: lengths at stride 2
   int64_t off = 0;
-  for (int r = 0; r < R; ++r) {
-    const int n = hdr_len[2 * (size_t)r];
-    if (n < 0) return fail("portion header: negative cols");
-    off += n;
-  }
+  const int solved_w = c->step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
+  OK(check_header(rows, R, c->fac_rows[solved_w], &off));
   s.ratings = off;
   if (R > 0) { s.first_row = rows[1]; s.last_row = rows[1 + 2 * (size_t)(R - 1)]; }
   const PlanCfg cfg{c->dual_max, c->split_cols, c->fused_max};
@@ -731,9 +984,11 @@ int stage_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const f
   s.view.row_len = (const int32_t*)(d + o_len);
   s.view.indx = (const int32_t*)(d + o_indx);
   s.view.vals = (const float*)(d + o_vals);
+  s.view.guard = c->d_bad;
   s.d_pfirst = (const int32_t*)(d + o_pf);
   s.plan_base = (const int32_t*)(d + o_plan);
   s.slot = &sl;
+  OK(launch_validate_cols(c, s.view.indx, off, c->fac_rows[1 - solved_w]));
   return 0;
 }
 
@@ -744,13 +999,7 @@ int stage_rmse_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, co
   if (R < 0) return fail("portion header: negative row count");
   s.n_rows = R;
   int64_t off = 0;
-  int32_t any_neg = 0;
-  for (int r = 0; r < R; ++r) {
-    const int32_t n = rows[2 + 2 * (size_t)r];
-    any_neg |= n;
-    off += n;
-  }
-  if (any_neg < 0) return fail("portion header: negative cols");
+  OK(check_header(rows, R, c->fac_rows[YCNR_USER_FACTORS], &off));   // RMSE rows are always users (EmfMaster.js:520-529)
   s.ratings = off;
   if (R > 0) { s.first_row = rows[1]; s.last_row = rows[1 + 2 * (size_t)(R - 1)]; }
   const int nb = (R + ycnr::kUnpackRowsPerBlock - 1) / ycnr::kUnpackRowsPerBlock;
@@ -767,8 +1016,8 @@ int stage_rmse_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, co
   size_t o_indx = al(o_bs + (size_t)(nb + 1) * 8);
   size_t o_vals = al(o_indx + (size_t)off * 4);
   size_t o_sums = al(o_vals + (size_t)off * 4);
-  // sums: row_sums[R][2] | portion_sums[3] | chunk_sums[ceil(R / chunk)][3]
-  size_t dev_total = al(o_sums + ((size_t)(2 * R + 3) + 3 * ((size_t)R / ycnr::kRmseChunkRows + 2)) * 8);
+  // sums: row_sums[R][3] | portion_sums[4] | chunk_sums[ceil(R / chunk)][4]
+  size_t dev_total = al(o_sums + ((size_t)(3 * R + 4) + 4 * ((size_t)R / ycnr::kRmseChunkRows + 2)) * 8);
 
   Slot& sl = c->slots[c->next_slot];
   c->next_slot = (c->next_slot + 1) % kSlots;
@@ -840,10 +1089,12 @@ int stage_rmse_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, co
   s.view.row_len = (const int32_t*)(d + o_len);
   s.view.indx = (const int32_t*)(d + o_indx);
   s.view.vals = (const float*)(d + o_vals);
+  s.view.guard = c->d_bad;
   s.d_sums = (double*)(d + o_sums);
   s.d_pfirst = (const int32_t*)(d + o_pf);
   s.plan_base = nullptr;
   s.slot = &sl;
+  OK(launch_validate_cols(c, s.view.indx, off, c->fac_rows[YCNR_ITEM_FACTORS]));
   return 0;
 }
 
@@ -856,7 +1107,10 @@ int finish_slot(ycnr_ctx* c, Slot* sl) {
 void collect_profile(ycnr_ctx* c) {
   for (auto& r : c->prof_open) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) c->prof.ms[r.cls] += ms;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      c->prof.ms[r.cls] += ms;
+      if (r.sub >= 0) c->dual_bin_ms[r.sub] += ms;
+    }
     c->ev_pool.push_back(r.a);
     c->ev_pool.push_back(r.b);
   }
@@ -886,11 +1140,14 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   if (o->use_double_precision)
     return fail("useDoublePrecision=true is not supported: the B200 path computes in float32 only (EmfBase.js:112)");
   if (o->lowmem) return fail("lowmem=true (file-backed factors, EmfBase.js:116) is not supported by the GPU path");
-  if (o->factors_count <= 0 || o->factors_count > 128)
-    return fail("factorsCount %d outside the supported range 1..128", o->factors_count);
+  if (o->factors_count <= 0 || o->factors_count > 256)
+    return fail("factorsCount %d outside the supported range 1..256", o->factors_count);
+  if (o->factors_count > 128 && ((o->factors_count & 3) || o->gram_path == YCNR_GRAM_FFMA))
+    return fail("factorsCount %d > 128 runs on the tensor-core Gram only: it needs factorsCount %% 4 == 0 and gramPath auto or tc",
+                o->factors_count);
   if (o->total_users <= 0 || o->total_items <= 0) return fail("totalUsersCount/totalItemsCount must be positive");
-  if (o->gram_path == YCNR_GRAM_TC3XTF32 && ((o->factors_count & 3) || o->factors_count > 124))
-    return fail("gram_path=TC3XTF32 needs factorsCount %% 4 == 0 and <= 124 (got %d)", o->factors_count);
+  if (o->gram_path == YCNR_GRAM_TC3XTF32 && ((o->factors_count & 3) || o->factors_count < 8))
+    return fail("gram_path=TC3XTF32 needs factorsCount %% 4 == 0 and >= 8 (got %d)", o->factors_count);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0)
@@ -910,6 +1167,9 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   c->split_cols = cfg.split_cols;
   c->fused_max = cfg.fused_max;
   c->use_tc = use_tc;
+  // systems wider than one tensor-core pass keep nb (nb - 1) / 2 sets of tile partials: bound them by working
+  // through the split rows in up to 8 groups (launch_primal_blocks)
+  if (use_tc && c->k > 124 && c->opts.solve_chunks < 2) c->opts.solve_chunks = kMaxChunks;
   c->num_sms = prop.multiProcessorCount;
   c->trace = getenv("YCNR_TRACE") != nullptr;
   if (const char* e = getenv("YCNR_SPREAD_BULK")) c->spread_bulk = atoi(e) ? 1 : 0;
@@ -928,6 +1188,11 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   }
   for (auto& e : c->chunk_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (int w = 0; w < 2; ++w) CU(cudaMalloc(&c->d_fac[w], (size_t)c->fac_rows[w] * c->k * sizeof(float)));
+  CU(cudaMalloc(&c->d_bad, sizeof(int32_t)));
+  CU(cudaMemset(c->d_bad, 0, sizeof(int32_t)));
+  CU(cudaMallocHost(&c->h_bad, sizeof(int32_t)));
+  *c->h_bad = 0;
+  g_default_ctx = c;
   *out = c;
   return 0;
 }
@@ -945,13 +1210,20 @@ int ycnr_destroy(ycnr_ctx* c) {
     if (c->h_registered[w]) cudaHostUnregister(c->h_fac[w]);
     if (c->d_fac[w]) cudaFree(c->d_fac[w]);
   }
-  for (auto& rs : c->rowsets) { rs.rows.release(); rs.ratings.release(); rs.plan.release(); rs.sums.release(); }
+  for (auto& rs : c->rowsets) {
+    rs.rows.release(); rs.ratings.release(); rs.plan.release(); rs.sums.release();
+    if (rs.h_sums) cudaFreeHost(rs.h_sums);
+    if (rs.sums_ready) cudaEventDestroy(rs.sums_ready);
+  }
   for (auto& s : c->slots) {
     if (s.host) cudaFreeHost(s.host);
     s.dev.release();
     if (s.done) cudaEventDestroy(s.done);
     if (s.solved) cudaEventDestroy(s.solved);
   }
+  if (g_default_ctx == c) g_default_ctx = nullptr;
+  if (c->d_bad) cudaFree(c->d_bad);
+  if (c->h_bad) cudaFreeHost(c->h_bad);
   c->partial.release();
   c->gather_tmp.release();
   c->table.buf.release();
@@ -1072,6 +1344,7 @@ int ycnr_start_train_step(ycnr_ctx* c, int32_t step_type) {
   c->step_type = step_type;
   c->solved_ranges.clear();
   const int solved = step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
+  c->fac_version[solved]++;   // peers may store into this replica during the step even if no portion arrives here
   OK(ensure_fixed_current(c, 1 - solved));
   OK(ensure_fixed_current(c, solved));  // rows that are not solved keep their values
   return 0;
@@ -1136,6 +1409,7 @@ int ycnr_end_train_step(ycnr_ctx* c) {
       i = j;
     }
   }
+  CU(cudaMemcpyAsync(c->h_bad, c->d_bad, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   const double ts0 = now_ms();
   CU(cudaStreamSynchronize(c->stream));
   const double ts1 = now_ms();
@@ -1152,6 +1426,13 @@ int ycnr_end_train_step(ycnr_ctx* c) {
   }
   c->solved_ranges.clear();
   c->step_type = -1;
+  if (*c->h_bad) {
+    *c->h_bad = 0;
+    CU(cudaMemset(c->d_bad, 0, sizeof(int32_t)));
+    return fail("ycnr_als_portion: a portion of this step held a column id outside the fixed factor matrix "
+                "(0..%lld); its rows and those of the portions queued after it were not solved",
+                (long long)c->fac_rows[1 - solved] - 1);
+  }
   return 0;
 }
 
@@ -1174,14 +1455,20 @@ int ycnr_rmse_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, con
   OK(set_device(c));
   StagedPortion s;
   OK(stage_rmse_portion(c, rows, indx, vals, s));
-  double sums[3] = {0, 0, 0};
+  double sums[4] = {0, 0, 0, 0};
   if (s.n_rows > 0) {
-    double* d_portion = s.d_sums + 2 * (size_t)s.n_rows;
-    OK(run_rmse(c, s.view, s.n_rows, s.ratings, c->rmse_shift, s.d_sums, s.d_pfirst, 1, d_portion, d_portion + 3));
+    double* d_portion = s.d_sums + 3 * (size_t)s.n_rows;
+    OK(run_rmse(c, s.view, s.n_rows, s.ratings, c->rmse_shift, s.d_sums, s.d_pfirst, 1, d_portion, d_portion + 4));
     CU(cudaMemcpyAsync(sums, d_portion, sizeof(sums), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_bad, c->d_bad, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   }
   OK(finish_slot(c, s.slot));
   CU(cudaStreamSynchronize(c->stream));
+  if (*c->h_bad) {
+    *c->h_bad = 0;
+    CU(cudaMemset(c->d_bad, 0, sizeof(int32_t)));
+    return fail("ycnr_rmse_portion: item id outside the item factor matrix (0..%lld)", (long long)c->fac_rows[1] - 1);
+  }
   memset(info, 0, sizeof(*info));
   info->rows_from = s.first_row;
   info->rows_cnt = s.n_rows;
@@ -1193,6 +1480,10 @@ int ycnr_rmse_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, con
   return 0;
 }
 
+// Compatibility export (upstream never calls it from lib/).  When `fixed` is one of the attached
+// factor matrices and its device replica is current, the rows are gathered from the replica and only the ids
+// travel up; any other host matrix is gathered row by row with the copy engine (cols copies of k floats) —
+// never a full upload of `fixed`.
 int ycnr_s_als_build_sub_fixed_facts(ycnr_ctx* c, float* sub, const float* fixed, int64_t fixed_rows,
                                      const int32_t* indx, int32_t cols, int32_t k) {
   if (!c || !sub || !fixed || !indx || cols < 0 || k <= 0) return fail("ycnr_s_als_build_sub_fixed_facts: bad argument");
@@ -1200,24 +1491,78 @@ int ycnr_s_als_build_sub_fixed_facts(ycnr_ctx* c, float* sub, const float* fixed
   for (int i = 0; i < cols; ++i)
     if (indx[i] < 0 || indx[i] >= fixed_rows) return fail("ycnr_s_als_build_sub_fixed_facts: index %d out of range", indx[i]);
   OK(set_device(c));
-  const size_t fb = (size_t)fixed_rows * k * sizeof(float), sb = (size_t)cols * k * sizeof(float);
+  const size_t sb = (size_t)cols * k * sizeof(float);
   auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  OK(c->gather_tmp.ensure(al(fb) + al(sb) + al((size_t)cols * sizeof(int32_t))));
+  OK(c->gather_tmp.ensure(al(sb) + al((size_t)cols * sizeof(int32_t))));
   char* d = (char*)c->gather_tmp.p;
-  float* d_fixed = (float*)d;
-  float* d_sub = (float*)(d + al(fb));
-  int32_t* d_idx = (int32_t*)(d + al(fb) + al(sb));
-  CU(cudaMemcpyAsync(d_fixed, fixed, fb, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(d_idx, indx, (size_t)cols * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  {
+  float* d_sub = (float*)d;
+  int32_t* d_idx = (int32_t*)(d + al(sb));
+  int attached = -1;
+  for (int w = 0; w < 2; ++w)
+    if (fixed == c->h_fac[w] && k == c->k && fixed_rows == c->fac_rows[w] && c->device_current[w]) attached = w;
+  if (attached >= 0) {
+    CU(cudaMemcpyAsync(d_idx, indx, (size_t)cols * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     ProfScope ps(c, YCNR_K_GATHER, cols, cols);
     const int64_t total = (int64_t)cols * k;
-    const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
-    ycnr::gather_rows_kernel<<<grid, 256, 0, c->stream>>>(d_sub, d_fixed, d_idx, cols, k);
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c->num_sms * 8);
+    ycnr::gather_rows_kernel<<<grid, 256, 0, c->stream>>>(d_sub, c->d_fac[attached], d_idx, cols, k);
+    CU(cudaGetLastError());
+  } else {
+    for (int i = 0; i < cols; ++i)
+      CU(cudaMemcpyAsync(d_sub + (size_t)i * k, fixed + (size_t)indx[i] * k, (size_t)k * sizeof(float),
+                         cudaMemcpyHostToDevice, c->stream));
   }
-  CU(cudaGetLastError());
   CU(cudaMemcpyAsync(sub, d_sub, sb, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ycnr_s_als_build_sub_fixed_facts_noctx(float* sub, const float* fixed, int64_t fixed_rows, const int32_t* indx,
+                                           int32_t cols, int32_t k) {
+  if (!g_default_ctx) return fail("sAlsBuildSubFixedFacts: no live context in this process (call ycnr_create first)");
+  return ycnr_s_als_build_sub_fixed_facts(g_default_ctx, sub, fixed, fixed_rows, indx, cols, k);
+}
+
+int ycnr_check_portion(const int32_t* rows, int64_t rows_len, int64_t indx_len, int64_t vals_len) {
+  if (!rows || rows_len < 1) return fail("portion: the rows array needs at least the row count");
+  const int64_t R = rows[0];
+  if (R < 0) return fail("portion header: negative row count");
+  if (2 * R + 1 > rows_len) return fail("portion header: %lld rows do not fit the rows array (%lld words)", (long long)R, (long long)rows_len);
+  int64_t off = 0;
+  for (int64_t r = 0; r < R; ++r) {
+    const int32_t n = rows[2 + 2 * r];
+    if (n < 0) return fail("portion header: negative cols in row %lld", (long long)r);
+    off += n;
+  }
+  if (off > indx_len || off > vals_len)
+    return fail("portion header: %lld ratings do not fit the indx/vals arrays (%lld / %lld)", (long long)off, (long long)indx_len, (long long)vals_len);
+  return 0;
+}
+
+int ycnr_factor_elems(ycnr_ctx* c, int32_t which, int64_t* out) {
+  if (!c || which < 0 || which > 1 || !out) return fail("ycnr_factor_elems: bad argument");
+  *out = c->fac_rows[which] * (int64_t)c->k;
+  return 0;
+}
+
+int ycnr_memory_usage(ycnr_ctx* c, int64_t out[4]) {
+  if (!c || !out) return fail("ycnr_memory_usage: bad argument");
+  OK(set_device(c));
+  size_t dev = 0, pinned = 0;
+  for (int w = 0; w < 2; ++w) {
+    dev += (size_t)c->fac_rows[w] * c->k * sizeof(float);
+    if (c->h_registered[w]) pinned += (size_t)c->fac_rows[w] * c->k * sizeof(float);
+  }
+  for (auto& rs : c->rowsets) dev += rs.rows.cap + rs.ratings.cap + rs.plan.cap + rs.sums.cap;
+  for (auto& sl : c->slots) { dev += sl.dev.cap; pinned += sl.host_cap; }
+  dev += c->table.buf.cap + c->ingest_tmp.cap + c->partial.cap + c->gather_tmp.cap;
+  for (auto& r : c->pinned) pinned += r.second;
+  size_t fr = 0, tot = 0;
+  CU(cudaMemGetInfo(&fr, &tot));
+  out[0] = (int64_t)dev;
+  out[1] = (int64_t)pinned;
+  out[2] = (int64_t)fr;
+  out[3] = (int64_t)tot;
   return 0;
 }
 
@@ -1291,7 +1636,7 @@ int ycnr_rowset_create(ycnr_ctx* c, int32_t step_type, int32_t n_rows, const int
     OK(rs.plan.ensure(packed.size() * 4));
     CU(cudaMemcpyAsync(rs.plan.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, c->stream));
   } else {
-    OK(rs.sums.ensure(((size_t)2 * n_rows + 3 * (size_t)n_portions + 4) * sizeof(double)));
+    OK(rs.sums.ensure(((size_t)3 * n_rows + 4 * (size_t)n_portions + 4) * sizeof(double)));
   }
   CU(cudaStreamSynchronize(c->stream));  // host sources may be freed by the caller on return
   *out = id;
@@ -1304,6 +1649,11 @@ int ycnr_rowset_destroy(ycnr_ctx* c, int32_t id) {
   CU(cudaStreamSynchronize(c->stream));
   RowSet& rs = c->rowsets[id];
   rs.rows.release(); rs.ratings.release(); rs.plan.release(); rs.sums.release();
+  if (rs.h_sums) cudaFreeHost(rs.h_sums);
+  if (rs.sums_ready) cudaEventDestroy(rs.sums_ready);
+  rs.h_sums = nullptr;
+  rs.sums_ready = nullptr;
+  rs.pending = rs.cached = false;
   rs.used = false;
   return 0;
 }
@@ -1316,35 +1666,71 @@ int ycnr_als_rowset(ycnr_ctx* c, int32_t id) {
   const int solved = rs.step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
   OK(ensure_fixed_current(c, 1 - solved));
   OK(ensure_fixed_current(c, solved));
+  c->fac_version[solved]++;   // (a rank without rows still receives its peers' rows)
   if (rs.n_rows == 0) return 0;
   const bool spread = c->spread_bulk < 0 ? rs.n_rows < kSpreadBulkRows : c->spread_bulk != 0;
   return run_als(c, rs.step_type, rs.view, rs.dplan, (const int32_t*)rs.plan.p, spread);
 }
 
-int ycnr_rmse_rowset(ycnr_ctx* c, int32_t id, double shift, double* totals, double* portion_sums) {
-  if (!c || !totals || id < 0 || id >= (int)c->rowsets.size() || !c->rowsets[id].used) return fail("ycnr_rmse_rowset: bad argument");
+// Queue the RMSE pass of a row set at `shift` (kernels + the copy of the per-portion sums), without waiting.
+// No-op when the sums of a pass over the same factor versions are already there or on their way.
+int ycnr_rmse_rowset_begin(ycnr_ctx* c, int32_t id, double shift) {
+  if (!c || id < 0 || id >= (int)c->rowsets.size() || !c->rowsets[id].used) return fail("ycnr_rmse_rowset_begin: bad argument");
   RowSet& rs = c->rowsets[id];
   if (rs.step_type != YCNR_RMSE_VALIDATE && rs.step_type != YCNR_RMSE_TEST) return fail("ycnr_rmse_rowset: row set is an ALS set");
   OK(set_device(c));
   OK(ensure_fixed_current(c, YCNR_USER_FACTORS));
   OK(ensure_fixed_current(c, YCNR_ITEM_FACTORS));
+  if (rs.n_rows == 0) return 0;
+  const bool fresh = rs.cache_ver[0] == c->fac_version[0] && rs.cache_ver[1] == c->fac_version[1];
+  if ((rs.cached || rs.pending) && fresh) return 0;
+  if (rs.pending) {   // a pass over older factors is still in flight: let it land before its buffers are reused
+    CU(cudaEventSynchronize(rs.sums_ready));
+    rs.pending = false;
+  }
+  if (!rs.h_sums) CU(cudaMallocHost(&rs.h_sums, sizeof(double) * 4 * rs.n_portions));
+  if (!rs.sums_ready) CU(cudaEventCreateWithFlags(&rs.sums_ready, cudaEventDisableTiming));
+  double* d_rows = (double*)rs.sums.p;
+  double* d_port = d_rows + 3 * (size_t)rs.n_rows;
+  OK(run_rmse(c, rs.view, rs.n_rows, rs.nnz, shift, d_rows, rs.d_portion_first, rs.n_portions, d_port));
+  CU(cudaMemcpyAsync(rs.h_sums, d_port, sizeof(double) * 4 * rs.n_portions, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(rs.sums_ready, c->stream));
+  rs.pending = true;
+  rs.cached = false;
+  rs.cache_shift = shift;
+  rs.cache_ver[0] = c->fac_version[0];
+  rs.cache_ver[1] = c->fac_version[1];
+  return 0;
+}
+
+int ycnr_rmse_rowset(ycnr_ctx* c, int32_t id, double shift, double* totals, double* portion_sums) {
+  if (!c || !totals || id < 0 || id >= (int)c->rowsets.size() || !c->rowsets[id].used) return fail("ycnr_rmse_rowset: bad argument");
+  OK(ycnr_rmse_rowset_begin(c, id, shift));
+  RowSet& rs = c->rowsets[id];
   totals[0] = totals[1] = totals[2] = 0.0;
   if (rs.n_rows == 0) {
     if (portion_sums) memset(portion_sums, 0, sizeof(double) * 3 * rs.n_portions);
     return 0;
   }
-  double* d_rows = (double*)rs.sums.p;
-  double* d_port = d_rows + 2 * (size_t)rs.n_rows;
-  OK(run_rmse(c, rs.view, rs.n_rows, rs.nnz, shift, d_rows, rs.d_portion_first, rs.n_portions, d_port));
-  std::vector<double> tmp;
-  double* hp = portion_sums;
-  if (!hp) { tmp.resize((size_t)3 * rs.n_portions); hp = tmp.data(); }
-  CU(cudaMemcpyAsync(hp, d_port, sizeof(double) * 3 * rs.n_portions, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  if (rs.pending) {
+    CU(cudaEventSynchronize(rs.sums_ready));
+    rs.pending = false;
+    rs.cached = true;
+  }
+  // the pass at `shift` from the sums at cache_shift: pred' = pred + d for every rating
+  const double d = shift - rs.cache_shift;
   for (int p = 0; p < rs.n_portions; ++p) {  // EmfMaster.m_completedPortion 770-774, portion order
-    totals[0] += hp[3 * p];
-    totals[1] += hp[3 * p + 1];
-    totals[2] += hp[3 * p + 2];
+    const double* q = rs.h_sums + 4 * (size_t)p;
+    const double d2 = d == 0.0 ? q[0] : q[0] - 2.0 * d * (q[3] - q[2]) + q[1] * d * d;
+    const double sp = d == 0.0 ? q[2] : q[2] + q[1] * d;
+    if (portion_sums) {
+      portion_sums[3 * p] = d2;
+      portion_sums[3 * p + 1] = q[1];
+      portion_sums[3 * p + 2] = sp;
+    }
+    totals[0] += d2;
+    totals[1] += q[1];
+    totals[2] += sp;
   }
   return 0;
 }
@@ -1507,7 +1893,11 @@ int ycnr_rowset_from_table(ycnr_ctx* c, int32_t step_type, uint32_t set_mask, in
   }
   const int64_t nnz_t = c->table.nnz;
   const int P = std::max(n_portions, 1);
-  const int n_chunks = (int)((nnz_t + ycnr::kItemChunk - 1) / ycnr::kItemChunk);
+  // by item: per-chunk counters of n_chunks x items words.  The chunk grows with the catalog so that the counters
+  // stay under 256 MB (100 M ratings x 1 M items would otherwise ask for 12 GB); the sort stays stable for any chunk.
+  int64_t item_chunk = ycnr::kItemChunk;
+  while (by_item && ((nnz_t + item_chunk - 1) / item_chunk) * (int64_t)items * 4 > ((int64_t)256 << 20)) item_chunk *= 2;
+  const int n_chunks = (int)((nnz_t + item_chunk - 1) / item_chunk);
   // scratch: cnt i32[rows] | ptr i64[rows+1] | block sums | pto | last_row | drop_last | flag | len | pos i64[rows+1]
   //          | (by item) chunk counters i32[n_chunks][items]
   const int nb = (rows + ycnr::kScanRowsPerBlock - 1) / ycnr::kScanRowsPerBlock + 2;
@@ -1540,7 +1930,7 @@ int ycnr_rowset_from_table(ycnr_ctx* c, int32_t step_type, uint32_t set_mask, in
   // 1. row lengths of the fetch and its row pointer
   if (by_item) {
     CU(cudaMemsetAsync(d_cur, 0, (size_t)n_chunks * items * 4, c->stream));
-    if (n_chunks) ycnr::item_hist_kernel<<<n_chunks, 256, 0, c->stream>>>(c->table.item, c->table.dt, set_mask, nnz_t, items, d_cur);
+    if (n_chunks) ycnr::item_hist_kernel<<<n_chunks, 256, 0, c->stream>>>(c->table.item, c->table.dt, set_mask, nnz_t, items, item_chunk, d_cur);
     ycnr::item_chunk_offsets_kernel<<<(items + 255) / 256, 256, 0, c->stream>>>(d_cur, n_chunks, items, d_cnt);
   } else {
     ycnr::count_by_user_kernel<<<(users + 7) / 8, 256, 0, c->stream>>>(c->table.user_ptr, c->table.dt, set_mask, users, d_cnt);
@@ -1568,7 +1958,7 @@ int ycnr_rowset_from_table(ycnr_ctx* c, int32_t step_type, uint32_t set_mask, in
   if (by_item) {
     if (n_chunks)
       ycnr::item_scatter_kernel<<<n_chunks, 32, 0, c->stream>>>(c->table.item, c->table.rating, c->table.dt, c->table.elem_user,
-                                                               set_mask, nnz_t, items, d_cur, d_ptr, (int32_t*)dr, (float*)(dr + o_vals));
+                                                               set_mask, nnz_t, items, item_chunk, d_cur, d_ptr, (int32_t*)dr, (float*)(dr + o_vals));
   } else {
     ycnr::fill_by_user_kernel<<<(users + 7) / 8, 256, 0, c->stream>>>(c->table.user_ptr, c->table.item, c->table.rating, c->table.dt,
                                                                      set_mask, users, d_ptr, (int32_t*)dr, (float*)(dr + o_vals));
@@ -1617,7 +2007,7 @@ int ycnr_rowset_from_table(ycnr_ctx* c, int32_t step_type, uint32_t set_mask, in
     CU(cudaMemcpyAsync(rs.plan.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   } else {
-    OK(rs.sums.ensure(((size_t)2 * n_rows + 3 * (size_t)P + 4) * sizeof(double)));
+    OK(rs.sums.ensure(((size_t)3 * n_rows + 4 * (size_t)P + 4) * sizeof(double)));
   }
   *out = id;
   return 0;
@@ -1758,6 +2148,18 @@ int ycnr_profile_reset(ycnr_ctx* c) {
   CU(cudaStreamSynchronize(c->stream));
   collect_profile(c);
   memset(&c->prof, 0, sizeof(c->prof));
+  memset(c->dual_bin_ms, 0, sizeof(c->dual_bin_ms));
+  memset(c->dual_bin_rows, 0, sizeof(c->dual_bin_rows));
+  return 0;
+}
+
+int ycnr_profile_dual_bins(ycnr_ctx* c, double* ms_out, int64_t* rows_out) {
+  if (!c || !ms_out || !rows_out) return fail("ycnr_profile_dual_bins: bad argument");
+  OK(set_device(c));
+  CU(cudaStreamSynchronize(c->stream));
+  collect_profile(c);
+  memcpy(ms_out, c->dual_bin_ms, sizeof(c->dual_bin_ms));
+  memcpy(rows_out, c->dual_bin_rows, sizeof(c->dual_bin_rows));
   return 0;
 }
 

@@ -93,12 +93,13 @@ class EmfBase:
         k = self.factorsCount
         self.userFactors[...] = front_end.init_factors(self.totalUsersCount, k, 0, seed)
         self.itemFactors[...] = front_end.init_factors(self.totalItemsCount, k, 1, seed)
-        if self.options["als"]["initFirstFactorAsAvgRating"]:
-            for mat, avg in ((self.userFactors, self.stats.get("ratingsAvgPerUser")),
-                             (self.itemFactors, self.stats.get("ratingsAvgPerItem"))):
-                if avg is not None:
-                    has = np.asarray(avg) > 0
-                    mat[has, 0] = np.asarray(avg, np.float32)[has]
+        if self.options["als"]["initFirstFactorAsAvgRating"]:       # EmfBase.js:500-511
+            for mat, key in ((self.userFactors, "ratingsAvgPerUser"), (self.itemFactors, "ratingsAvgPerItem")):
+                avg = self.stats.get(key)
+                if avg is None:
+                    raise ValueError("als.initFirstFactorAsAvgRating needs stats.%s (run splitDataForTrain first)" % key)
+                has = ~np.isnan(np.asarray(avg, np.float64))       # `avg !== undefined`
+                mat[has, 0] = np.asarray(avg, np.float32)[has]
 
     def openDevice(self):
         """Create the GPU context for this worker and mirror the factor segments on it."""

@@ -59,12 +59,17 @@ class EmfManager:
 
     # -- save -----------------------------------------------------------------------------------
     def saveCalcResults(self, calcInfo=None):
+        """Only rank 0 touches the directories (every rank holds the same replicas after a half-step): with
+        several ranks the rmtree/rename below would race.  calcCnt is the caller's business — upstream bumps it
+        once per train run (EmfLord.js:904), not per save."""
         m = self.m
         if m.options["gpu"]["bulk"] and m.ctx is not None:
             m.syncFactorsToHost()
         self.calcDate = time.strftime("%Y-%m-%dT%H:%M:%S")
-        self.calcCnt += 1
         info = calcInfo or self.getCalcInfo()
+        if getattr(m, "rank", 0) != 0:
+            self.lastCalcInfo = info
+            return info
         if os.path.isdir(self.factorsTempPath):
             shutil.rmtree(self.factorsTempPath)
         os.makedirs(self.factorsTempPath)
@@ -120,9 +125,13 @@ class EmfManager:
         options.checkpointEveryIter also after every iteration."""
         m = self.m
         n = m.options["trainIters"] if iters is None else iters
+        self.calcCnt += 1                                   # once per run (EmfLord.js:904)
+        saved = False
         for _ in range(n):
             m.trainIter()
-            if m.options.get("checkpointEveryIter"):
+            saved = bool(m.options.get("checkpointEveryIter"))
+            if saved:
                 self.saveCalcResults()
-        self.saveCalcResults()
+        if not saved:                                       # the last iteration's checkpoint IS the final state
+            self.saveCalcResults()
         return m.history

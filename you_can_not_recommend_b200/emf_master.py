@@ -56,6 +56,7 @@ class EmfMaster(EmfBase):
         self.sharedHost = False
         self._ranges = {}
         self.phase_ms = {}
+        self._workerMU = []
 
     # ---- prepare ---------------------------------------------------------------------------
     def splitDataForTrain(self):
@@ -65,8 +66,11 @@ class EmfMaster(EmfBase):
             fe.split_sets(t, o["dataSetDistr"], seed=o["seed"] + 1)
         self.totalUsersCount, self.totalItemsCount = t.users, t.items   # max(id), Q5
         cu, ci = t.counts_per_user(), t.counts_per_item()
+        # avg_rating of EmfLord.getStats (EmfLord.js:67-78, 95-119); only als.initFirstFactorAsAvgRating reads it
+        au, ai = (t.avg_per_user(), t.avg_per_item()) if o["als"]["initFirstFactorAsAvgRating"] else (None, None)
         self.stats = {
             "ratingsCntPerUser": cu, "ratingsCntPerItem": ci,
+            "ratingsAvgPerUser": au, "ratingsAvgPerItem": ai,   # NaN = upstream's `undefined` (row.cnt == 0)
             "maxRatingsPerUser": int(cu.max()), "maxRatingsPerItem": int(ci.max()),
             "trainUsersRatingsCount": int(cu.sum(dtype=np.int64)),
             "trainItemsRatingsCount": int(ci.sum(dtype=np.int64)),
@@ -132,6 +136,7 @@ class EmfMaster(EmfBase):
         wp.peer, mp.peer = mp, wp
         mp.on("completedPortion", self.wm_completedPortion)
         mp.on("preparedToTrain", lambda d: None)
+        mp.on("setMemoryUsage", lambda d: self._workerMU.append(d["mu"]))
         mp.on("endedTrainStep", lambda d: None)
         w = EmfWorker(0, wp, o)
         w.master_side = mp
@@ -240,6 +245,16 @@ class EmfMaster(EmfBase):
         self.userFactors, self.itemFactors = ydist.node_shared_matrices(
             tag, [(self.totalUsersCount, k), (self.totalItemsCount, k)], self.rank, init, self.group)
         self.sharedHost = True
+
+    def getMemoryUsage(self):
+        """EmfBase.getMemoryUsage (EmfBase.js:880-900): [factor segments ("shm"), this process' rss, one rss per
+        worker]; the workers answer 'getMemoryUsage' with 'setMemoryUsage' (EmfWorker.js:43,109-113)."""
+        import resource
+        self._workerMU = []
+        for w in self.workers:
+            w.master_side.emit("getMemoryUsage")
+        shm = sum(int(a.nbytes) for a in (self.userFactors, self.itemFactors) if a is not None)
+        return [shm, resource.getrusage(resource.RUSAGE_SELF).ru_maxrss * 1024] + [mu["rss"] for mu in self._workerMU]
 
     def endTrain(self):
         for w in self.workers:
@@ -384,6 +399,14 @@ class EmfMaster(EmfBase):
         """One pass of the loop body of EmfLord.train (EmfLord.js:892-902)."""
         self._timed("byUser", self.alsTrainStep, "byUser")
         self._timed("byItem", self.alsTrainStep, "byItem")
+        if self.options["gpu"]["bulk"]:
+            # the validate and the test pass both run with shift 0 (EmfMaster.js:389-402): queue them together, the
+            # calcRmse calls below only collect; the third pass is derived from the second on the host
+            d = self.options["dataSetDistr"]
+            for step, pct in (("rmseValidate", d[1]), ("rmseTest", d[2])):
+                lo, hi = self.my_portions[step]
+                if pct and hi > lo:
+                    self.ctx.rmse_rowset_begin(self.rowsets[step], 0.0)
         out = {
             "rmseValidate": self._timed("rmseValidate", self.calcRmse, "rmseValidate", False),
             "rmseTest": self._timed("rmseTest", self.calcRmse, "rmseTest", False),

@@ -50,6 +50,7 @@ class EmfWorker(EmfBase):
         self._status = "ready"
         p = self.process
         # handler table of EmfWorker.init (EmfWorker.js:43-51)
+        p.on("getMemoryUsage", self.mw_getMemoryUsage)
         p.on("prepareToTrain", self.mw_prepareToTrain)
         p.on("startTrain", self.mw_startTrain)
         p.on("endTrain", self.mw_endTrain)
@@ -59,6 +60,15 @@ class EmfWorker(EmfBase):
         p.on("calcTrainAlsPortion", self.mw_calcTrainAlsPortion)
         p.on("calcTrainSgdPortion", self.mw_calcTrainSgdPortion)
         p.on("calcRmsePortion", self.mw_calcRmsePortion)
+
+    def mw_getMemoryUsage(self, data=None):
+        """EmfWorker.mw_getMemoryUsage (EmfWorker.js:109-113): process.memoryUsage() of the worker, here the
+        resident set of this process plus what the context holds on the device and in page-locked memory."""
+        import resource
+        mu = {"rss": resource.getrusage(resource.RUSAGE_SELF).ru_maxrss * 1024, "heapTotal": 0, "heapUsed": 0}
+        if self.ctx is not None:
+            mu.update(self.ctx.memory_usage())
+        self.process.emit("setMemoryUsage", {"mu": mu})
 
     # -- lifecycle (EmfWorker.js:119-164) -------------------------------------------------
     def mw_prepareToTrain(self, data):

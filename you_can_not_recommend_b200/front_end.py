@@ -113,6 +113,22 @@ class RatingsTable:
         m = (self.dataset_type >= 1) & (self.dataset_type <= 3)
         return np.bincount(self.item_ids[m], minlength=self.items).astype(np.int32)
 
+    def avg_per_user(self):
+        """avg_rating per user over sets 1,2,3 (malrec_users.avg_rating as doUpdateStats leaves it,
+        EmfLord.js:255-397); NaN where the user has no such rating (upstream: row skipped -> undefined)."""
+        m = (self.dataset_type >= 1) & (self.dataset_type <= 3)
+        cs = np.zeros(self.nnz + 1, np.float64)
+        np.cumsum(np.where(m, self.ratings, 0).astype(np.float64), out=cs[1:])
+        s = cs[self.user_ptr[1:]] - cs[self.user_ptr[:-1]]
+        c = self.counts_per_user()
+        return np.where(c > 0, s / np.maximum(c, 1), np.nan)
+
+    def avg_per_item(self):
+        m = (self.dataset_type >= 1) & (self.dataset_type <= 3)
+        s = np.bincount(self.item_ids[m], weights=self.ratings[m].astype(np.float64), minlength=self.items)
+        c = self.counts_per_item()
+        return np.where(c > 0, s / np.maximum(c, 1), np.nan)
+
     def total_ratings_avg(self):
         # "select avg(r.rating) where dataset_type in (1,2,3)"  EmfLord.js:224-228
         m = (self.dataset_type >= 1) & (self.dataset_type <= 3)

@@ -109,6 +109,13 @@ napi_value AttachFactors(napi_env env, napi_callback_info info) {
   if (!args(env, info, 3, a) || !handle(env, a[0], &c) || !typed(env, a[1], napi_float32_array, &u, &nu) ||
       !typed(env, a[2], napi_float32_array, &v, &nv))
     return nullptr;
+  int64_t want_u = 0, want_v = 0;
+  if (!check(env, ycnr_factor_elems(c, YCNR_USER_FACTORS, &want_u)) || !check(env, ycnr_factor_elems(c, YCNR_ITEM_FACTORS, &want_v)))
+    return nullptr;
+  if ((int64_t)nu < want_u || (int64_t)nv < want_v) {
+    fail(env, "attachFactors: factor arrays are smaller than total x factorsCount");
+    return nullptr;
+  }
   check(env, ycnr_attach_factors(c, u, v));
   return undefined(env);
 }
@@ -148,6 +155,7 @@ napi_value AlsPortion(napi_env env, napi_callback_info info) {
       !typed(env, a[2], napi_int32_array, &indx, &n1) || !typed(env, a[3], napi_float32_array, &vals, &n2))
     return nullptr;
   ycnr_portion_info pi;
+  if (!check(env, ycnr_check_portion(rows, (int64_t)n0, (int64_t)n1, (int64_t)n2))) return nullptr;
   if (!check(env, ycnr_als_portion(c, rows, indx, vals, &pi))) return nullptr;
   return portion_result(env, pi, false);
 }
@@ -182,25 +190,51 @@ napi_value RmsePortion(napi_env env, napi_callback_info info) {
       !typed(env, a[2], napi_int32_array, &indx, &n1) || !typed(env, a[3], napi_float32_array, &vals, &n2))
     return nullptr;
   ycnr_portion_info pi;
+  if (!check(env, ycnr_check_portion(rows, (int64_t)n0, (int64_t)n1, (int64_t)n2))) return nullptr;
   if (!check(env, ycnr_rmse_portion(c, rows, indx, vals, &pi))) return nullptr;
   return portion_result(env, pi, true);
 }
 
-// sAlsBuildSubFixedFacts(handle, sub, fixed, indx, cols, k) — upstream signature + the context
+// sAlsBuildSubFixedFacts(sub, fixed, indx, cols, k) — upstream's own signature (cpp_utils/cpp_utils.js:15-19,
+// als_utils.cc:22-38): runs on the process's current context; a 6-argument call with the context handle first
+// is accepted as well.
 napi_value SAlsBuildSubFixedFacts(napi_env env, napi_callback_info info) {
   napi_value a[6];
-  ycnr_ctx* c;
+  size_t argc = 6;
+  if (napi_get_cb_info(env, info, &argc, a, nullptr, nullptr) != napi_ok || argc < 5) {
+    fail(env, "wrong number of arguments");
+    return nullptr;
+  }
+  const size_t o = argc >= 6 ? 1 : 0;
+  ycnr_ctx* c = nullptr;
   float *sub, *fixed;
   int32_t* indx;
   size_t ns, nf, ni;
   int32_t cols, k;
-  if (!args(env, info, 6, a) || !handle(env, a[0], &c) || !typed(env, a[1], napi_float32_array, &sub, &ns) ||
-      !typed(env, a[2], napi_float32_array, &fixed, &nf) || !typed(env, a[3], napi_int32_array, &indx, &ni) ||
-      napi_get_value_int32(env, a[4], &cols) != napi_ok || napi_get_value_int32(env, a[5], &k) != napi_ok)
+  if ((o && !handle(env, a[0], &c)) || !typed(env, a[o], napi_float32_array, &sub, &ns) ||
+      !typed(env, a[o + 1], napi_float32_array, &fixed, &nf) || !typed(env, a[o + 2], napi_int32_array, &indx, &ni) ||
+      napi_get_value_int32(env, a[o + 3], &cols) != napi_ok || napi_get_value_int32(env, a[o + 4], &k) != napi_ok)
     return nullptr;
   if (k <= 0 || cols < 0 || (size_t)cols > ni || (size_t)cols * (size_t)k > ns) return fail(env, "buffer too small"), nullptr;
-  check(env, ycnr_s_als_build_sub_fixed_facts(c, sub, fixed, (int64_t)(nf / (size_t)k), indx, cols, k));
+  if (o) check(env, ycnr_s_als_build_sub_fixed_facts(c, sub, fixed, (int64_t)(nf / (size_t)k), indx, cols, k));
+  else check(env, ycnr_s_als_build_sub_fixed_facts_noctx(sub, fixed, (int64_t)(nf / (size_t)k), indx, cols, k));
   return undefined(env);
+}
+
+// getMemoryUsage(handle) -> {device, pinned, deviceFree, deviceTotal}   (EmfWorker.mw_getMemoryUsage, EmfWorker.js:109-113)
+napi_value GetMemoryUsage(napi_env env, napi_callback_info info) {
+  napi_value a[1];
+  ycnr_ctx* c;
+  if (!args(env, info, 1, a) || !handle(env, a[0], &c)) return nullptr;
+  int64_t mu[4];
+  if (!check(env, ycnr_memory_usage(c, mu))) return nullptr;
+  napi_value o, v;
+  napi_create_object(env, &o);
+  napi_create_int64(env, mu[0], &v); napi_set_named_property(env, o, "device", v);
+  napi_create_int64(env, mu[1], &v); napi_set_named_property(env, o, "pinned", v);
+  napi_create_int64(env, mu[2], &v); napi_set_named_property(env, o, "deviceFree", v);
+  napi_create_int64(env, mu[3], &v); napi_set_named_property(env, o, "deviceTotal", v);
+  return o;
 }
 
 napi_value DAlsBuildSubFixedFacts(napi_env env, napi_callback_info) {
@@ -390,6 +424,7 @@ napi_value Init(napi_env env, napi_value exports) {
       {"rmsePortion", nullptr, RmsePortion, nullptr, nullptr, nullptr, 0, nullptr},
       {"sAlsBuildSubFixedFacts", nullptr, SAlsBuildSubFixedFacts, nullptr, nullptr, nullptr, 0, nullptr},
       {"dAlsBuildSubFixedFacts", nullptr, DAlsBuildSubFixedFacts, nullptr, nullptr, nullptr, 0, nullptr},
+      {"getMemoryUsage", nullptr, GetMemoryUsage, nullptr, nullptr, nullptr, 0, nullptr},
       {"tableUpload", nullptr, TableUpload, nullptr, nullptr, nullptr, 0, nullptr},
       {"tableSplit", nullptr, TableSplit, nullptr, nullptr, nullptr, 0, nullptr},
       {"tableCounts", nullptr, TableCounts, nullptr, nullptr, nullptr, 0, nullptr},

@@ -22,10 +22,12 @@ EXPORTS = [
     "ycnr_last_error", "ycnr_device_count", "ycnr_create", "ycnr_destroy", "ycnr_attach_factors",
     "ycnr_upload_factors", "ycnr_download_factors", "ycnr_invalidate_device", "ycnr_device_factors",
     "ycnr_stream", "ycnr_synchronize", "ycnr_host_register", "ycnr_host_unregister", "ycnr_start_train_step", "ycnr_als_portion", "ycnr_end_train_step",
-    "ycnr_start_calc_rmse", "ycnr_rmse_portion", "ycnr_s_als_build_sub_fixed_facts", "ycnr_rowset_create",
-    "ycnr_rowset_destroy", "ycnr_als_rowset", "ycnr_rmse_rowset", "ycnr_ipc_export", "ycnr_ipc_import",
+    "ycnr_start_calc_rmse", "ycnr_rmse_portion", "ycnr_s_als_build_sub_fixed_facts", "ycnr_s_als_build_sub_fixed_facts_noctx",
+    "ycnr_check_portion", "ycnr_factor_elems", "ycnr_memory_usage", "ycnr_rowset_create",
+    "ycnr_rowset_destroy", "ycnr_als_rowset", "ycnr_rmse_rowset", "ycnr_rmse_rowset_begin", "ycnr_ipc_export", "ycnr_ipc_import",
     "ycnr_ipc_close", "ycnr_set_peers", "ycnr_table_upload", "ycnr_table_split", "ycnr_table_counts", "ycnr_rowset_from_table",
     "ycnr_rowset_info", "ycnr_rowset_read", "ycnr_recommend_batch", "ycnr_debug_plan", "ycnr_debug_read_partials", "ycnr_profile_reset", "ycnr_profile_read",
+    "ycnr_profile_dual_bins",
 ]
 
 
@@ -106,6 +108,12 @@ def debug_plan(row_len, factors_count=100, gram_path=GRAM_AUTO, dual_max_cols=-1
             "item_order": words[summ[31]:summ[31] + n_items].copy()}
 
 
+def build_sub_fixed_facts_noctx(sub, fixed, indx, cols, k):
+    """cpp_utils.sAlsBuildSubFixedFacts(sub, fixed, indx, cols, k) with upstream's own arity (cpp_utils.js:15-19)."""
+    _check(lib().ycnr_s_als_build_sub_fixed_facts_noctx(_f32(sub), _f32(fixed), C.c_int64(fixed.size // k), _i32(indx),
+                                                        C.c_int32(cols), C.c_int32(k)))
+
+
 def device_count():
     n = C.c_int32(0)
     rc = lib().ycnr_device_count(C.byref(n))
@@ -179,6 +187,7 @@ class Context:
 
     def als_portion(self, rows, indx, vals):
         info = PortionInfo()
+        _check(lib().ycnr_check_portion(_i32(rows), C.c_int64(len(rows)), C.c_int64(len(indx)), C.c_int64(len(vals))))
         _check(lib().ycnr_als_portion(self._h, _i32(rows), _i32(indx), _f32(vals), C.byref(info)))
         return info
 
@@ -190,6 +199,7 @@ class Context:
 
     def rmse_portion(self, rows, indx, vals):
         info = PortionInfo()
+        _check(lib().ycnr_check_portion(_i32(rows), C.c_int64(len(rows)), C.c_int64(len(indx)), C.c_int64(len(vals))))
         _check(lib().ycnr_rmse_portion(self._h, _i32(rows), _i32(indx), _f32(vals), C.byref(info)))
         return info
 
@@ -197,6 +207,12 @@ class Context:
         k = fixed.shape[1]
         _check(lib().ycnr_s_als_build_sub_fixed_facts(self._h, _f32(sub), _f32(fixed), C.c_int64(fixed.shape[0]),
                                                       _i32(indx), C.c_int32(len(indx)), C.c_int32(k)))
+
+    def memory_usage(self):
+        """'getMemoryUsage': dict of device / page-locked bytes held by the context and free / total device memory."""
+        out = (C.c_int64 * 4)()
+        _check(lib().ycnr_memory_usage(self._h, out))
+        return {"device": out[0], "pinned": out[1], "deviceFree": out[2], "deviceTotal": out[3]}
 
     # -- bulk path
     def rowset_create(self, step_type, row_ids, row_start, row_len, indx, vals, portion_first=None):
@@ -213,6 +229,9 @@ class Context:
 
     def als_rowset(self, rowset):
         _check(lib().ycnr_als_rowset(self._h, C.c_int32(rowset)))
+
+    def rmse_rowset_begin(self, rowset, shift):
+        _check(lib().ycnr_rmse_rowset_begin(self._h, C.c_int32(rowset), C.c_double(shift)))
 
     def rmse_rowset(self, rowset, shift, n_portions=0):
         totals = (C.c_double * 3)()
@@ -309,6 +328,12 @@ class Context:
     # -- measurement
     def profile_reset(self):
         _check(lib().ycnr_profile_reset(self._h))
+
+    def profile_dual_bins(self):
+        ms = (C.c_double * 24)()
+        rows = (C.c_int64 * 24)()
+        _check(lib().ycnr_profile_dual_bins(self._h, ms, rows))
+        return [(mt + 1, ms[mt], rows[mt]) for mt in range(24) if rows[mt]]
 
     def profile_read(self):
         p = Profile()
