@@ -38,7 +38,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mal", choices=["mal", "netflix", "ml-1m", "ml-100k"])
     ap.add_argument("--factors", type=int, default=0)
-    ap.add_argument("--e2e-portion", type=int, default=8_000_000, help="ratingsInPortionForAls of the e2e leg")
+    ap.add_argument("--e2e-portion", type=int, default=10_000,
+                    help="ratingsInPortionForAls / ForRmse of the headline e2e leg (reference default: 10 000, EmfBase.js:97-103)")
+    ap.add_argument("--e2e-large-portion", type=int, default=8_000_000, help="portion size of the secondary e2e leg (0 = skip)")
+    ap.add_argument("--e2e-python-steps", type=int, default=1,
+                    help="timed iterations of the e2e leg driven by Python worker messages at --e2e-portion (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -102,6 +106,17 @@ def measured_peaks():
         return float(p["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def pipe_peaks():
+    """TF32 tensor-pipe and FP32 FFMA peaks measured on a B200 of this pool with scripts/micro/tf32_mma_rate.cu and
+    ffma_rate.cu (profiles/pipe_peaks.json); the profiling recipe's nominal dense figure when the file is missing."""
+    try:
+        p = json.load(open(os.path.join(ROOT, "profiles", "pipe_peaks.json")))
+        return {"tf32_tflops": float(p["tf32_mma_tflops_n256"]), "ffma_tflops": float(p.get("ffma_tflops", 56.0)),
+                "source": "measured (profiles/pipe_peaks.json)"}
+    except Exception:
+        return {"tf32_tflops": 1100.0, "ffma_tflops": 56.0, "source": "fallback (B200_PROFILING.md nominal dense tf32)"}
 
 
 def measured_traffic(workload, k, cls):
@@ -314,20 +329,47 @@ def main():
         return prof[c]["ms"] / (args.steps or 1)
     dom = max(native.KERNEL_CLASSES, key=kernel_ms)
     roof = None
+    pk = pipe_peaks()
     if prof[dom]["launches"] > 0 and prof[dom]["ms"] > 0:
         per_launch_ms = prof[dom]["ms"] / prof[dom]["launches"]
         ratings_per_launch = prof[dom]["ratings"] / prof[dom]["launches"]
         alg_bytes = ratings_per_launch * k * 4                  # B_gather = nnz * k * 4
         alg_flops = ratings_per_launch * k * k                  # F_gram = nnz * k^2 (symmetric-aware)
-        achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": measured_traffic(args.workload, k, dom) if world == 1 else None,
+        # what the kernel really executes per rating: the tensor-core Gram issues M = 128 x N = 2 NC MMAs (K = 8 ratings
+        # each) whatever k is; the FFMA kernels execute the padded lower triangle of 4 x 4 tiles
+        kp = 4 * ((k + 3) // 4)
+        if dom == "gram_tc":
+            kv = kp if k <= 124 else 2 * {3: 44}.get((k + 59) // 60, 52 if ((k + 59) // 60) * 52 >= k else 60)
+            exec_flops = ratings_per_launch * 2.0 * 128 * 2 * ((kv + 4 + 7) // 8 * 8)
+            pipe, pipe_peak = "tensor (tcgen05 kind::tf32)", pk["tf32_tflops"]
+        else:
+            exec_flops = ratings_per_launch * 2.0 * (kp * (kp + 4) / 2 + kp)
+            pipe, pipe_peak = "fp32 ffma", pk["ffma_tflops"]
+        t_hbm = alg_bytes / (peak * 1e9) * 1e3
+        t_pipe = exec_flops / (pipe_peak * 1e12) * 1e3
+        bound = "hbm" if t_hbm >= t_pipe else "tensor"
+        if bound == "hbm":
+            achieved, rpeak, unit = alg_bytes / (per_launch_ms * 1e-3) / 1e9, peak, "GB/s"
+        else:
+            achieved, rpeak, unit = alg_flops / (per_launch_ms * 1e-3) / 1e12, pipe_peak * alg_flops / exec_flops, "TFLOP/s"
+        step_bytes = sum(nnz_by.values()) * k * 4               # both half-steps of the iteration, algorithmic
+        roof = {"bound": bound, "kernel": dom, "achieved": achieved, "peak": rpeak, "unit": unit,
+                "frac": achieved / rpeak, "traffic": measured_traffic(args.workload, k, dom) if world == 1 else None,
                 "traffic_source": "profiles/traffic_%s.json (ncu --set full, dram read+write per launch)" % args.workload,
-                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                "peak_source": (peak_src + " (MEASURED_PEAKS.json hbm_gbs)") if bound == "hbm" else
+                               pk["source"] + ", scaled by algorithmic / executed flops",
                 "launch_ms": per_launch_ms, "launches_timed": prof[dom]["launches"],
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "gram_tflops": alg_flops / (per_launch_ms * 1e-3) / 1e12,
-                "share_of_step": prof[dom]["ms"] / ms if ms > 0 else None}
+                "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": alg_flops,
+                "terms": {"hbm": {"ms_at_peak": t_hbm, "peak_gbs": peak, "frac": t_hbm / per_launch_ms},
+                          "pipe": {"pipe": pipe, "executed_flops_per_launch": exec_flops, "peak_tflops": pipe_peak,
+                                   "executed_over_algorithmic": exec_flops / alg_flops, "ms_at_peak": t_pipe,
+                                   "frac": t_pipe / per_launch_ms, "peak_source": pk["source"]}},
+                "roofline_ms": max(t_hbm, t_pipe), "frac_of_max_term": max(t_hbm, t_pipe) / per_launch_ms,
+                "share_of_step": prof[dom]["ms"] / ms if ms > 0 else None,
+                "whole_step": {"algorithmic_bytes": step_bytes, "ms": ms_per_step,
+                               "achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                               "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                               "note": "gathered factor bytes of both half-steps on rank 0 / iteration time (RMSE passes included in the time) / HBM peak"}}
     kernels = {c: {"ms_per_step": prof[c]["ms"] / args.steps, "launches_per_step": prof[c]["launches"] / args.steps,
                    "rows_per_step": prof[c]["rows"] / args.steps, "ratings_per_step": prof[c]["ratings"] / args.steps}
                for c in native.KERNEL_CLASSES if prof[c]["launches"]}
@@ -335,48 +377,62 @@ def main():
     m.endTrain()
     del m
 
-    # ---------------- e2e: worker messages with host portion buffers ----------------
-    e2e = None
-    if not args.no_e2e:
+    # ---------------- e2e: the worker's per-portion entry points with host portion buffers ----------------
+    def run_e2e(portion, native_loop, n_steps, n_warm):
         opts2 = {"factorsCount": k,
-                 "ratingsInPortionForAls": {"byUser": args.e2e_portion, "byItem": args.e2e_portion},
-                 "ratingsInPortionForRmse": args.e2e_portion,
+                 "ratingsInPortionForAls": {"byUser": portion, "byItem": portion},
+                 "ratingsInPortionForRmse": portion,
                  "gpu": {"bulk": False, "profile": False, "device": local, "gramPath": args.gram,
-                         "cachePortions": True}}
+                         "cachePortions": True, "nativeLoop": native_loop}}
         m2 = EmfMaster(table, opts2, rank=rank, world=world)
         m2.prepareToTrain()
         if world > 1 and args.fused_peers:
             m2.connectPeers()
-        for _ in range(max(1, min(args.warmup, 2))):
+        for _ in range(n_warm):
             m2.trainIter()
         m2.ctx.synchronize()
         torch.cuda.synchronize()
         barrier()
         m2.h2d_bytes = m2.d2h_bytes = 0
         m2.phase_ms = {}
-        n_e2e = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            m2.trainIter()
+        for _ in range(n_steps):
+            last2 = m2.trainIter()
         m2.ctx.synchronize()
         torch.cuda.synchronize()
         barrier()
-        e2e_s = (time.perf_counter() - t0) / n_e2e
-        h2d, d2h = m2.h2d_bytes / n_e2e, m2.d2h_bytes / n_e2e
+        e2e_s = (time.perf_counter() - t0) / n_steps
+        h2d, d2h = m2.h2d_bytes / n_steps, m2.d2h_bytes / n_steps
+        calls = sum(m2.my_portions[s_][1] - m2.my_portions[s_][0] for s_ in ("byUser", "byItem", "rmseValidate", "rmseTest", "rmseTest"))
         if world > 1:
             tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_s = float(tt[0])
-            bb = torch.tensor([h2d, d2h], device="cuda", dtype=torch.float64)
+            bb = torch.tensor([h2d, d2h, calls], device="cuda", dtype=torch.float64)
             dist.all_reduce(bb)
-            h2d, d2h = float(bb[0]), float(bb[1])
-        e2e = {"value": table.nnz / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "ratings_in_portion": args.e2e_portion,
-               "phase_ms": {k_: v_ / n_e2e for k_, v_ in m2.phase_ms.items()},
-               "api": "EmfWorker calcTrainAlsPortion/calcRmsePortion messages -> ycnr_als_portion/ycnr_rmse_portion",
-               "inputs": "converted portions cached in page-locked host memory (usePortionsCache); H2D of every portion and D2H of the solved rows inside the timed region"}
+            h2d, d2h, calls = float(bb[0]), float(bb[1]), int(bb[2])
+        out = {"value": table.nnz / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_s * 1e3, "steps": n_steps, "ratings_in_portion": portion,
+               "portion_calls_per_step": calls,
+               "phase_ms": {k_: v_ / n_steps for k_, v_ in m2.phase_ms.items()},
+               "rmse": last2,
+               "api": ("ycnr_als_portion / ycnr_rmse_portion_async, one call per portion, issued by a native loop "
+                       "(ycnr_als_portions / ycnr_rmse_portions_async)") if native_loop else
+                      "EmfWorker calcTrainAlsPortion / calcRmsePortion messages (Python mirror) -> ycnr_als_portion / ycnr_rmse_portion_async",
+               "inputs": "converted portions cached in page-locked host memory (usePortionsCache taken to its limit: the "
+                         "conversion of EmfMaster.js:571-614 is outside the timed region); H2D of every portion and D2H of "
+                         "the solved rows into the host factor segments inside it"}
         m2.endTrain()
         del m2
+        return out
+
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args.e2e_portion, True, max(1, args.steps), max(1, min(args.warmup, 2)))
+        if args.e2e_large_portion:
+            e2e["large_portions"] = run_e2e(args.e2e_large_portion, False, max(1, min(args.steps, 3)), 1)
+        if args.e2e_python_steps:
+            e2e["python_messages"] = run_e2e(args.e2e_portion, False, args.e2e_python_steps, 1)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

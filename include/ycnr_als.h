@@ -161,6 +161,23 @@ int ycnr_start_calc_rmse(ycnr_ctx* ctx, int32_t step_type, double global_avg_shi
 int ycnr_rmse_portion(ycnr_ctx* ctx, const int32_t* rmse_rows, const int32_t* rmse_indx,
                       const float* rmse_vals, ycnr_portion_info* info_out);
 
+/* Portions of fewer than 2^20 ratings (the reference default is 10 000, EmfBase.js:97-103) are QUEUED by
+ * ycnr_als_portion and launched in batches of ~4 M ratings (or at ycnr_end_train_step): the call returns the
+ * 'completedPortion' fields at once, the rows are in the host segment after ycnr_end_train_step as before.
+ * The RMSE twin: ycnr_rmse_portion_async queues a portion under a caller tag (portionNo); ycnr_rmse_poll hands
+ * back the completed portions in the order they were queued — wait != 0 flushes the queue and waits for all of
+ * them (the worker's 'completedPortion' replies are asynchronous messages upstream as well, EmfWorker.js:304-314).
+ * ycnr_rmse_portion itself stays synchronous. */
+int ycnr_rmse_portion_async(ycnr_ctx* ctx, const int32_t* rmse_rows, const int32_t* rmse_indx, const float* rmse_vals,
+                            int64_t tag);
+int ycnr_rmse_poll(ycnr_ctx* ctx, int32_t wait, int32_t max_out, int64_t* tags_out, ycnr_portion_info* infos_out,
+                   int32_t* n_out);
+/* n per-portion calls issued from native code: the same entry points, without the binding's per-call cost. */
+int ycnr_als_portions(ycnr_ctx* ctx, int32_t n, const int32_t* const* rows, const int32_t* const* indx,
+                      const float* const* vals, ycnr_portion_info* infos_out);
+int ycnr_rmse_portions_async(ycnr_ctx* ctx, int32_t n, const int32_t* const* rows, const int32_t* const* indx,
+                             const float* const* vals, const int64_t* tags);
+
 /* cpp_utils.sAlsBuildSubFixedFacts(sub, fixed, indx, cols, k): sub[c,:] = fixed[indx[c],:].
  * 'fixed' is a host matrix of fixed_rows x k floats. */
 int ycnr_s_als_build_sub_fixed_facts(ycnr_ctx* ctx, float* sub, const float* fixed, int64_t fixed_rows,
@@ -200,6 +217,8 @@ int ycnr_als_rowset(ycnr_ctx* ctx, int32_t rowset);
  * the last pass are kept per row set together with the sum of the ratings, so a pass with ANOTHER shift over
  * unchanged factors (EmfLord.js:898) is derived on the host: sum (r-p-d)^2 = sum (r-p)^2 - 2d (sum r - sum p) + n d^2. */
 int ycnr_rmse_rowset_begin(ycnr_ctx* ctx, int32_t rowset, double global_avg_shift);
+/* Sum of the ratings of the row set / of its last portion, from the last pass (see ycnr_rmse_rowset_begin). */
+int ycnr_rmse_rowset_ratings(ycnr_ctx* ctx, int32_t rowset, double* total_out, double* last_portion_out);
 /* totals[3] = {rSumDiff2, rCnt, rSum}; portion_sums[n_portions*3] optional. Synchronous. */
 int ycnr_rmse_rowset(ycnr_ctx* ctx, int32_t rowset, double global_avg_shift, double* totals,
                      double* portion_sums);

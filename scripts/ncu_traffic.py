@@ -1,8 +1,8 @@
 """DRAM traffic per launch and per kernel class from `ncu --set full` reports (raw page):
 usage: python scripts/ncu_traffic.py out.json rep1.ncu-rep [rep2.ncu-rep ...]"""
 import csv, json, subprocess, sys
-CLASS = [("gram_tc_kernel", "gram_tc"), ("als_dual_kernel", "dual_fused"), ("rmse_rows_kernel", "rmse_rows"),
-         ("rmse_portion_reduce", "rmse_reduce"), ("als_primal_kernel", "reduce_solve")]
+CLASS = [("gram_tc_kernel", "gram_tc"), ("als_dual", "dual_fused"), ("rmse_rows_kernel", "rmse_rows"),
+         ("rmse_portion_reduce", "rmse_reduce"), ("als_primal_kernel", "reduce_solve"), ("als_solve_blocks", "reduce_solve")]
 agg = {}
 for rep in sys.argv[2:]:
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout

@@ -25,6 +25,26 @@ def test_balanced_cuts_properties():
     assert list(ydist.balanced_cuts(np.zeros(0, np.int64), 2)) == [0, 0, 0]
 
 
+def test_cost_model_cuts():
+    """Row cost model behind the rank cuts: a row is not worth its nnz — a 1-rating row still costs
+    a launch slot, the dual cost grows with n^3, every long row carries one k x k factorisation — and cuts made on
+    the cumulative cost balance the cost, not the nnz."""
+    c = ydist.row_cost(np.asarray([0, 1, 4, 48, 96, 97, 1000, 100000]), 100)
+    assert c[0] == 0 and (np.diff(c[1:5]) > 0).all() and c[5] < c[4] * 1.2 and c[6] > c[5] and c[7] > 100 * c[5]
+    assert c[1] * 96 > 2 * c[4] and c[4] > 4 * c[3]
+    assert ydist.row_cost(np.asarray([200]), 256)[0] > 10 * ydist.row_cost(np.asarray([200]), 100)[0]
+    rng = np.random.default_rng(1)
+    counts = np.concatenate([rng.integers(1, 8, 5000), rng.integers(300, 900, 300)])      # short rows first, long last
+    pto = np.arange(10, len(counts) + 1, 10)
+    ends = ydist.cost_ends(counts, pto, 100)
+    cuts = ydist.balanced_cuts(ends, 2)
+    cost = ydist.row_cost(counts, 100)
+    a = cost[:pto[cuts[1] - 1]].sum()
+    assert abs(a - cost.sum() / 2) < 0.05 * cost.sum()
+    nnz_cuts = ydist.balanced_cuts(np.cumsum(counts)[pto - 1], 2)
+    assert nnz_cuts[1] != cuts[1]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -50,6 +70,8 @@ def _worker(rank, world, port, q):
     ranges = ydist.all_ranges((a, b), world)
     ydist.broadcast_ranges(mat, ranges)
     sums, last = ydist.reduce_rmse((1.0 + rank, 10.0 * (rank + 1), 0.5), {"rSum": float(rank), "rCnt": 2.0} if rank == 0 or hi > lo else None)
+    gathered = ydist.all_gather_doubles([float(rank), 0.5, 10.0 * (rank + 1)])
+    assert gathered == [[0.0, 0.5, 10.0], [1.0, 0.5, 20.0]]
     q.put((rank, ranges, mat.numpy().copy(), sums, last))
     dist.barrier()
     dist.destroy_process_group()

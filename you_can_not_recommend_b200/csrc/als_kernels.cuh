@@ -493,6 +493,7 @@ struct DualArgs {
   double lambda;
   DstList dst;
   const int32_t* __restrict__ work;
+  int bar_off;  // als_dual_kernel: float offset of the gather mbarrier inside its dynamic shared memory
 };
 
 constexpr int kDualMaxSplit = 8;   // largest K-split of the Gram sweep (k = 100: 25 chunks of 4 columns)
@@ -532,13 +533,22 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
   // Rating r (= row 4I+i of the system) is staged in slot i*mt + I: the four rows of a tile
   // sit mt slots apart, so lanes owning consecutive tiles read consecutive slots and the
   // LDS.128 of the Gram loop are bank-conflict free (pitch/4 is odd).
-  if ((k & 3) == 0) {
+  const bool bulk = (k & 3) == 0;
+  const uint32_t bar = smem_u32(dsm + a.bar_off);   // 8 bytes behind every other array
+  if (bulk) {   // TMA bulk copies, one per rated row (see als_dual_tpt_kernel)
+    if (tid == 0) {
+      tma_mbar_init(bar, 1);
+      tma_mbar_expect_tx(bar, (uint32_t)n * (uint32_t)k * 4u);
+    }
     const int CH = k >> 2;
-    for (int q = tid; q < np * CH; q += NT) {
-      const int r = q / CH, c = q - r * CH;
-      const bool ok = r < n;
-      const int col = ok ? __ldg(a.rows.indx + beg + r) : 0;
-      cp_async16(Y + ((r & 3) * mt + (r >> 2)) * pitch + 4 * c, a.fixed + (size_t)col * k + 4 * c, ok ? 16 : 0);
+    for (int q = tid; q < (np - n) * CH; q += NT) {
+      const int r = n + q / CH, c = q % CH;
+      *reinterpret_cast<float4*>(Y + ((r & 3) * mt + (r >> 2)) * pitch + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int r = tid; r < n; r += NT) {
+      const int col = __ldg(a.rows.indx + beg + r);
+      tma_bulk_g2s(Y + ((r & 3) * mt + (r >> 2)) * pitch, a.fixed + (size_t)col * k, (uint32_t)k * 4u, bar);
     }
   } else {
     for (int q = tid; q < np * K4; q += NT) {
@@ -551,6 +561,7 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
   for (int r = tid; r < np; r += NT) vs[r] = r < n ? __ldg(a.rows.vals + beg + r) : 0.f;
   cp_async_commit();
   cp_async_wait<0>();
+  if (bulk) tma_mbar_wait(bar, 0);
   __syncthreads();
 
   // ---- G tiles ------------------------------------------------------------------------
@@ -718,13 +729,24 @@ __global__ void __launch_bounds__(NT) als_dual_tpt_kernel(const DualArgs a) {
   constexpr int mt = MT;
   constexpr int np = 4 * MT;
 
-  if ((k & 3) == 0) {
+  const bool bulk = (k & 3) == 0;
+  const uint32_t bar = smem_u32(vs + NMAX);       // 8 bytes behind the scratch vectors (16-byte aligned)
+  if (bulk) {
+    // TMA bulk copies: one cp.async.bulk per rated row (k * 4 bytes, 16-byte aligned on both sides) instead of
+    // k / 4 cp.async instructions; their bytes complete the mbarrier
+    if (tid == 0) {
+      tma_mbar_init(bar, 1);
+      tma_mbar_expect_tx(bar, (uint32_t)n * (uint32_t)k * 4u);
+    }
     const int CH = k >> 2;
-    for (int q = tid; q < np * CH; q += NT) {
-      const int r = q / CH, c = q - r * CH;
-      const bool ok = r < n;
-      const int col = ok ? __ldg(a.rows.indx + beg + r) : 0;
-      cp_async16(Y + ((r & 3) * mt + (r >> 2)) * pitch + 4 * c, a.fixed + (size_t)col * k + 4 * c, ok ? 16 : 0);
+    for (int q = tid; q < (np - n) * CH; q += NT) {            // padding rows of the last tile: zero
+      const int r = n + q / CH, c = q % CH;
+      *reinterpret_cast<float4*>(Y + ((r & 3) * mt + (r >> 2)) * pitch + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();                                          // barrier initialised and armed
+    for (int r = tid; r < n; r += NT) {
+      const int col = __ldg(a.rows.indx + beg + r);
+      tma_bulk_g2s(Y + ((r & 3) * mt + (r >> 2)) * pitch, a.fixed + (size_t)col * k, (uint32_t)k * 4u, bar);
     }
   } else {
     for (int q = tid; q < np * K4; q += NT) {
@@ -746,6 +768,7 @@ __global__ void __launch_bounds__(NT) als_dual_tpt_kernel(const DualArgs a) {
   }
   float acc[TPT][4][4];
   cp_async_wait<0>();
+  if (bulk) tma_mbar_wait(bar, 0);
   __syncthreads();
 
   const float lam = (float)(a.lambda * (double)n);

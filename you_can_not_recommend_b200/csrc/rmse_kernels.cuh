@@ -27,6 +27,9 @@ struct RmseArgs {
   int n_rows;
   double shift;
   double* __restrict__ row_sums;  // [n_rows][3] = {sum diff^2, sum pred, sum rating}
+  // optional: rows in processing order, longest first, so that the four groups of a warp walk rows of (nearly)
+  // the same length — validate / test rows are power-law distributed and a warp lives as long as its longest row
+  const int32_t* __restrict__ order;
 };
 
 constexpr int kRmseRowSums = 3;
@@ -35,11 +38,12 @@ constexpr int kRmsePortionSums = 4;   // rSumDiff2, rCnt, rSum, sum of ratings
 // NQ = float4 chunks of the factor row per lane (k <= 32 NQ); NQ = 0: any k, scalar loads
 template <int NQ>
 __global__ void __launch_bounds__(256) rmse_rows_kernel(const RmseArgs a) {
-  const int g = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 3);   // row of this 8-lane group
+  const int g0 = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 3);   // this 8-lane group's position
   const int lane = threadIdx.x & 31;
   const int gl = lane & 7;
   const uint32_t gmask = 0xFFu << (lane & 24);
-  if (g >= a.n_rows) return;                 // whole groups leave together
+  if (g0 >= a.n_rows) return;                // whole groups leave together
+  const int g = a.order ? __ldg(a.order + g0) : g0;
   if (rows_poisoned(a.rows)) {               // a column id of the portion is out of range: no gather
     if (gl == 0) { a.row_sums[3 * (size_t)g] = 0.0; a.row_sums[3 * (size_t)g + 1] = 0.0; a.row_sums[3 * (size_t)g + 2] = 0.0; }
     return;

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -241,7 +242,12 @@ struct RowSet {
   DevBuf rows;      // row_ids | row_len | portion_first (int32) then row_start (int64), packed
   DevBuf ratings;   // indx (int32) | vals (float)
   DevBuf plan;      // DevPlan words
-  DevBuf sums;      // rmse: row_sums [R][2] | portion_sums [P][3]
+  DevBuf sums;      // rmse: row_sums [R][3] | portion_sums [P][4]
+  DevBuf order;     // rmse: entries longest first
+  DevBuf erows;     // rmse: work entries (rows cut into <= kRmseChunk ratings): start i64 | ids | len | efirst[P+1]
+  RowsView eview{};
+  const int32_t* d_efirst = nullptr;
+  int n_entries = 0;
   RowsView view{};
   const int32_t* d_portion_first = nullptr;
   DevPlan dplan;
@@ -258,12 +264,59 @@ struct RowSet {
 struct Slot {  // staging for the per-portion path
   void* host = nullptr;
   size_t host_cap = 0;
+  void* host2 = nullptr;      // batches of small portions: row arrays start | ids | len
+  size_t host2_cap = 0;
+  void* host3 = nullptr;      // batches: portion firsts + launch plan (host -> device) / RMSE sums (device -> host)
+  size_t host3_cap = 0;
+  int inflight = -1;          // index into ycnr_ctx::rmse_inflight of the RMSE batch whose sums land in host3
   DevBuf dev;
   cudaEvent_t done = nullptr;
   cudaEvent_t solved = nullptr;   // kernels of the portion finished: its rows may be copied back
   bool pending = false;
 };
 constexpr int kSlots = 4;
+
+// ---- batches of small portions ------------------------------------------------------------------------
+// The reference hands the worker ~10 000 ratings per message (ratingsInPortionForAls, EmfBase.js:97-103): about 150
+// user rows, microseconds of GPU work.  Portions below kBatchDirectRatings are therefore QUEUED: the call checks the
+// header, appends the rows to the open batch (ratings of page-locked, address-adjacent cache buffers are only
+// noted as DMA segments, others are copied into the slot) and returns; the batch goes to the device as ONE launch
+// group when it holds kBatchFlushRatings ratings, when a large portion arrives, or when the step ends.
+constexpr int64_t kBatchFlushRatings = (int64_t)4 << 20;
+constexpr int64_t kBatchDirectRatings = (int64_t)1 << 20;
+
+struct BatchSeg {
+  const int32_t* indx;
+  const float* vals;
+  int64_t n;
+  int64_t dev_off;     // first rating of the segment in the batch's device arrays
+  int64_t stage_off;   // staged segments: offset inside the slot's staging arrays
+  bool direct;         // page-locked caller memory: DMA'd from where it lies
+};
+
+struct Batch {
+  int kind = 0;        // 0 = closed, 1 = ALS, 2 = RMSE
+  Slot* slot = nullptr;
+  int32_t* ids = nullptr;                            // row arrays, in the slot's page-locked host2
+  int32_t* len = nullptr;
+  int64_t* start = nullptr;
+  size_t n_rows = 0, cap_rows = 0;
+  std::vector<int32_t> pfirst;                       // RMSE: first entry of every portion
+  std::vector<int64_t> tags;                         // RMSE: caller's tag per portion
+  std::vector<ycnr_portion_info> infos;              // RMSE: rows_from / rows_cnt / ratings per portion
+  std::vector<BatchSeg> segs;
+  std::vector<std::pair<int32_t, int32_t>> ranges;   // ALS: [first, last] row id per portion
+  int64_t ratings = 0, staged = 0;
+};
+
+struct RmseInflight {
+  Slot* slot = nullptr;
+  cudaEvent_t done = nullptr;
+  std::vector<int64_t> tags;
+  std::vector<ycnr_portion_info> infos;
+  const double* h_sums = nullptr;                    // [P][4] in the slot's host3
+  bool live = false;
+};
 
 struct ProfRec {
   int cls;
@@ -324,6 +377,29 @@ struct ycnr_ctx {
   int32_t* h_bad = nullptr;   // page-locked
   Slot slots[kSlots];
   int next_slot = 0;
+  Batch batch;
+  size_t max_host3 = 0;   // largest plan block any slot has needed: every slot is grown to it at its next use
+  size_t max_slot_dev = 0;
+  size_t max_batch_rows = 0;
+  int64_t batch_flush_ratings = kBatchFlushRatings;   // YCNR_BATCH_FLUSH overrides (tests exercise many flushes)
+  std::vector<RmseInflight> rmse_inflight;
+  std::vector<int> rmse_order;                                    // live entries of rmse_inflight, oldest first
+  std::vector<std::pair<int64_t, ycnr_portion_info>> rmse_done;   // completed, not yet polled (FIFO)
+  size_t rmse_done_head = 0;
+  // Per-portion sums {rSumDiff2, rCnt, rSum, sum of ratings} of the previous RMSE pass, by tag (portionNo): the
+  // third pass of an iteration (EmfLord.js:898: same test portions, shift applied, factors untouched) is answered
+  // from them — sum (r-p-d)^2 = sum (r-p)^2 - 2d (sum r - sum p) + n d^2 — without touching the device again.
+  struct PortionSums {
+    int32_t rows_from, rows_cnt;
+    int64_t ratings;
+    double d2, cnt, pred, rat;
+  };
+  struct RmsePass {
+    int step_type = -1;
+    double shift = 0.0;
+    uint64_t ver[2] = {0, 0};
+    std::unordered_map<int64_t, PortionSums> sums;   // by tag
+  } rmse_prev, rmse_cur;
   // per-portion step state
   int step_type = -1;
   double rmse_shift = 0.0;
@@ -694,7 +770,8 @@ int launch_dual_bin(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t 
   a.work = work;
   int red = 0;
   for (int mt = 1; mt <= MT_MAX; ++mt) red = std::max(red, dual_red_floats(mt, NT));
-  const size_t smem = ((size_t)4 * MT_MAX * a.pitch + (MT_MAX + 1) * 16 + 16 * MT_MAX + 8 * MT_MAX + red) * sizeof(float);
+  a.bar_off = 4 * MT_MAX * a.pitch + (MT_MAX + 1) * 16 + 16 * MT_MAX + 8 * MT_MAX + red;   // multiple of 4 floats
+  const size_t smem = (size_t)a.bar_off * sizeof(float) + 16;
   if (smem > 48 * 1024) OK(ensure_dynamic_smem(c, reinterpret_cast<const void*>(&als_dual_kernel<MT_MAX, NT>), smem));
   ProfScope ps(c, YCNR_K_DUAL_FUSED, count, ratings, st, MT_MAX - 1);
   als_dual_kernel<MT_MAX, NT><<<count, NT, smem, st>>>(a);
@@ -721,7 +798,7 @@ int launch_dual_bin2(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t
   constexpr int NT = dual2_nt(MT), TPT = dual2_tpt(MT);
   DualArgs a = base;
   a.work = work;
-  const size_t smem = ((size_t)4 * MT * a.pitch + (MT + 1) * 16 + 16 * MT + 8 * MT) * sizeof(float);
+  const size_t smem = ((size_t)4 * MT * a.pitch + (MT + 1) * 16 + 16 * MT + 8 * MT) * sizeof(float) + 16;   // + gather mbarrier
   if (smem > 48 * 1024) OK(ensure_dynamic_smem(c, reinterpret_cast<const void*>(&als_dual_tpt_kernel<MT, NT, TPT>), smem));
   ProfScope ps(c, YCNR_K_DUAL_FUSED, count, ratings, st, MT - 1);
   als_dual_tpt_kernel<MT, NT, TPT><<<count, NT, smem, st>>>(a);
@@ -799,8 +876,49 @@ int run_als(ycnr_ctx* c, int step_type, const RowsView& view, const DevPlan& p, 
   return 0;
 }
 
+// RMSE work entries: one 8-lane group walks an entry sequentially, so a user row with thousands of validate ratings
+// would be a serial tail that no amount of GPUs shortens.  Rows longer than kRmseChunk ratings are cut into
+// entries of at most kRmseChunk (same row id, consecutive ratings); the per-portion reduction adds the entries'
+// sums in order, so the result stays deterministic.  efirst[p] = first entry of portion p.
+constexpr int kRmseChunk = 64;
+
+void expand_rmse_entries(const int32_t* ids, const int64_t* start, const int32_t* len, int n_rows, const int32_t* pfirst,
+                         int P, std::vector<int32_t>& eids, std::vector<int64_t>& estart, std::vector<int32_t>& elen,
+                         std::vector<int32_t>& efirst) {
+  eids.clear(); estart.clear(); elen.clear();
+  efirst.assign((size_t)P + 1, 0);
+  int p = 0;
+  for (int r = 0; r < n_rows; ++r) {
+    while (p < P && pfirst[p] <= r) efirst[p++] = (int32_t)eids.size();
+    int n = len[r];
+    int64_t st = start[r];
+    do {
+      const int m = std::min(n, kRmseChunk);
+      eids.push_back(ids[r]);
+      estart.push_back(st);
+      elen.push_back(m);
+      st += m;
+      n -= m;
+    } while (n > 0);
+  }
+  while (p <= P) efirst[p++] = (int32_t)eids.size();
+}
+
+// rows by length, longest first (stable counting sort; ties keep the row order)
+void rows_longest_first(const int32_t* len, int n_rows, int32_t* order) {
+  int mx = 0;
+  for (int r = 0; r < n_rows; ++r) mx = std::max(mx, len[r]);
+  const int nb = std::min(mx, 4095) + 1;
+  std::vector<int32_t> cnt(nb + 1, 0);
+  auto bucket = [&](int r) { return nb - 1 - std::min(std::max(len[r], 0), nb - 1); };
+  for (int r = 0; r < n_rows; ++r) cnt[bucket(r) + 1]++;
+  for (int b = 0; b < nb; ++b) cnt[b + 1] += cnt[b];
+  for (int r = 0; r < n_rows; ++r) order[cnt[bucket(r)]++] = r;
+}
+
 int run_rmse(ycnr_ctx* c, const RowsView& view, int n_rows, int64_t nnz, double shift, double* d_row_sums,
-             const int32_t* d_portion_first, int n_portions, double* d_portion_sums, double* d_chunk_sums = nullptr) {
+             const int32_t* d_portion_first, int n_portions, double* d_portion_sums, double* d_chunk_sums = nullptr,
+             const int32_t* d_order = nullptr) {
   if (n_rows <= 0 || n_portions <= 0) return 0;
   ycnr::RmseArgs a{};
   a.rows = view;
@@ -810,6 +928,7 @@ int run_rmse(ycnr_ctx* c, const RowsView& view, int n_rows, int64_t nnz, double 
   a.n_rows = n_rows;
   a.shift = shift;
   a.row_sums = d_row_sums;
+  a.order = d_order;
   {
     ProfScope ps(c, YCNR_K_RMSE_ROWS, n_rows, nnz);
     const int rows_per_cta = 32;   // one 8-lane group per row
@@ -832,6 +951,38 @@ int run_rmse(ycnr_ctx* c, const RowsView& view, int n_rows, int64_t nnz, double 
                                                                          d_portion_sums);
   }
   CU(cudaGetLastError());
+  return 0;
+}
+
+// Device copy of the RMSE work entries of a row set (host arrays of its rows given) + their processing order.
+int build_rmse_entries(ycnr_ctx* c, RowSet& rs, const int32_t* ids, const int64_t* start, const int32_t* len,
+                       const int32_t* pfirst) {
+  std::vector<int32_t> eids, elen, efirst, order;
+  std::vector<int64_t> estart;
+  expand_rmse_entries(ids, start, len, rs.n_rows, pfirst, rs.n_portions, eids, estart, elen, efirst);
+  const int E = (int)eids.size();
+  rs.n_entries = E;
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t o_ids = al((size_t)E * 8), o_len = al(o_ids + (size_t)E * 4), o_pf = al(o_len + (size_t)E * 4);
+  OK(rs.erows.ensure(al(o_pf + (size_t)(rs.n_portions + 1) * 4) + 16));
+  char* d = (char*)rs.erows.p;
+  if (E) {
+    CU(cudaMemcpyAsync(d, estart.data(), (size_t)E * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + o_ids, eids.data(), (size_t)E * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + o_len, elen.data(), (size_t)E * 4, cudaMemcpyHostToDevice, c->stream));
+    order.resize((size_t)E);
+    rows_longest_first(elen.data(), E, order.data());
+    OK(rs.order.ensure((size_t)E * 4));
+    CU(cudaMemcpyAsync(rs.order.p, order.data(), (size_t)E * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaMemcpyAsync(d + o_pf, efirst.data(), (size_t)(rs.n_portions + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  rs.eview = rs.view;
+  rs.eview.row_start = (const int64_t*)d;
+  rs.eview.row_ids = (const int32_t*)(d + o_ids);
+  rs.eview.row_len = (const int32_t*)(d + o_len);
+  rs.d_efirst = (const int32_t*)(d + o_pf);
+  OK(rs.sums.ensure(((size_t)3 * E + 4 * (size_t)rs.n_portions + 4) * sizeof(double)));
+  CU(cudaStreamSynchronize(c->stream));   // the host vectors go out of scope
   return 0;
 }
 
@@ -1104,6 +1255,340 @@ int finish_slot(ycnr_ctx* c, Slot* sl) {
   return 0;
 }
 
+bool region_pinned(ycnr_ctx* c, const void* p, size_t bytes) {
+  const char* q = (const char*)p;
+  for (auto& r : c->pinned)
+    if (q >= r.first && q + bytes <= r.first + r.second) return true;
+  return false;
+}
+
+int ensure_pinned(void** ptr, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return 0;
+  if (*ptr) cudaFreeHost(*ptr);
+  *ptr = nullptr;
+  *cap = 0;
+  const size_t want = bytes + bytes / 4 + 4096;
+  CU(cudaMallocHost(ptr, want));
+  *cap = want;
+  return 0;
+}
+
+// Move the sums of a finished RMSE batch into the completed queue (portion order).
+int drain_inflight(ycnr_ctx* c, int idx, bool wait) {
+  RmseInflight& f = c->rmse_inflight[idx];
+  if (!f.live) return 0;
+  if (!wait && cudaEventQuery(f.done) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  CU(cudaEventSynchronize(f.done));
+  for (size_t p = 0; p < f.tags.size(); ++p) {
+    ycnr_portion_info pi = f.infos[p];
+    pi.r_sum_diff2 = f.h_sums[4 * p];
+    pi.r_cnt = f.h_sums[4 * p + 1];
+    pi.r_sum = f.h_sums[4 * p + 2];
+    c->rmse_done.emplace_back(f.tags[p], pi);
+    c->rmse_cur.sums[f.tags[p]] = {pi.rows_from, pi.rows_cnt, pi.ratings_in_portion, f.h_sums[4 * p], f.h_sums[4 * p + 1],
+                                   f.h_sums[4 * p + 2], f.h_sums[4 * p + 3]};
+  }
+  f.live = false;
+  if (f.slot) f.slot->inflight = -1;
+  return 0;
+}
+
+int acquire_slot(ycnr_ctx* c, Slot** out) {
+  Slot& sl = c->slots[c->next_slot];
+  c->next_slot = (c->next_slot + 1) % kSlots;
+  const double tw0 = now_ms();
+  while (sl.inflight >= 0 && !c->rmse_order.empty()) {   // completions stay in flush order: drain the older ones first
+    const int idx = c->rmse_order.front();
+    OK(drain_inflight(c, idx, true));
+    c->rmse_order.erase(c->rmse_order.begin());
+  }
+  if (sl.pending) {
+    CU(cudaEventSynchronize(sl.done));
+    sl.pending = false;
+  }
+  c->t_slot_wait += now_ms() - tw0;
+  if (!sl.done) CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  if (!sl.solved) CU(cudaEventCreateWithFlags(&sl.solved, cudaEventDisableTiming));
+  *out = &sl;
+  return 0;
+}
+
+int batch_flush(ycnr_ctx* c);
+
+// Row arrays of the open batch live in the slot's page-locked host2 buffer (start i64[cap] | ids i32[cap] |
+// len i32[cap]) and are DMA'd from there: the per-row loop below is the only pass over the header.
+int batch_rows_reserve(ycnr_ctx* c, Batch& b, size_t need) {
+  if (need <= b.cap_rows) return 0;
+  const size_t cap = std::max<size_t>(std::max(need + need / 2, 2 * b.cap_rows), 65536);
+  void* nh = nullptr;
+  CU(cudaMallocHost(&nh, cap * 16));
+  int64_t* nstart = (int64_t*)nh;
+  int32_t* nids = (int32_t*)((char*)nh + cap * 8);
+  int32_t* nlen = (int32_t*)((char*)nh + cap * 12);
+  if (b.n_rows) {
+    memcpy(nstart, b.start, b.n_rows * 8);
+    memcpy(nids, b.ids, b.n_rows * 4);
+    memcpy(nlen, b.len, b.n_rows * 4);
+  }
+  if (b.slot->host2) cudaFreeHost(b.slot->host2);
+  b.slot->host2 = nh;
+  b.slot->host2_cap = cap * 16;
+  b.start = nstart;
+  b.ids = nids;
+  b.len = nlen;
+  b.cap_rows = cap;
+  return 0;
+}
+
+// Append one small portion (`off` ratings) to the open batch of `kind`; the header is checked on the way
+// (row ids inside [0, lim_rows) and strictly ascending, no negative lengths — see check_header).
+int batch_add(ycnr_ctx* c, int kind, const int32_t* rows, const int32_t* indx, const float* vals, int64_t off,
+              int64_t tag, ycnr_portion_info* info) {
+  Batch& b = c->batch;
+  if (b.kind != 0 && b.kind != kind) OK(batch_flush(c));
+  if (b.kind == 0) {
+    OK(acquire_slot(c, &b.slot));
+    OK(ensure_pinned(&b.slot->host, &b.slot->host_cap, (size_t)(c->batch_flush_ratings + kBatchDirectRatings) * 8));
+    b.kind = kind;
+    b.pfirst.clear(); b.tags.clear(); b.infos.clear(); b.segs.clear(); b.ranges.clear();
+    b.ratings = b.staged = 0;
+    b.n_rows = 0;
+    b.cap_rows = b.slot->host2_cap / 16;
+    b.start = (int64_t*)b.slot->host2;
+    b.ids = (int32_t*)((char*)b.slot->host2 + b.cap_rows * 8);
+    b.len = (int32_t*)((char*)b.slot->host2 + b.cap_rows * 12);
+    OK(batch_rows_reserve(c, b, c->max_batch_rows + c->max_batch_rows / 4 + 4096));
+  }
+  const int R = rows[0];
+  OK(batch_rows_reserve(c, b, b.n_rows + (size_t)R + (kind == 2 ? (size_t)(off / kRmseChunk) : 0)));
+  const int64_t base = b.ratings;
+  int64_t run = base;
+  if (kind == 2) b.pfirst.push_back((int32_t)b.n_rows);
+  const size_t r0 = b.n_rows;
+  {
+    int32_t* pid = b.ids + r0;
+    int32_t* pln = b.len + r0;
+    int64_t* pst = b.start + r0;
+    size_t e = 0;
+    if (kind == 1) {
+      for (int r = 0; r < R; ++r) {
+        const int32_t n = rows[2 + 2 * (size_t)r];
+        pid[r] = rows[1 + 2 * (size_t)r];
+        pln[r] = n;
+        pst[r] = run;
+        run += n;
+      }
+      e = (size_t)R;
+    } else {   // RMSE: rows cut into entries of at most kRmseChunk ratings (see expand_rmse_entries)
+      for (int r = 0; r < R; ++r) {
+        const int32_t id = rows[1 + 2 * (size_t)r];
+        int32_t n = rows[2 + 2 * (size_t)r];
+        do {
+          const int32_t m = n < kRmseChunk ? n : kRmseChunk;
+          pid[e] = id;
+          pln[e] = m;
+          pst[e] = run;
+          ++e;
+          run += m;
+          n -= m;
+        } while (n > 0);
+      }
+    }
+    b.n_rows = r0 + e;
+  }
+  const size_t n_added = b.n_rows - r0;
+  if (off > 0) {
+    const bool direct = region_pinned(c, indx, (size_t)off * 4) && region_pinned(c, vals, (size_t)off * 4);
+    BatchSeg* last = b.segs.empty() ? nullptr : &b.segs.back();
+    // The master's portion cache is the step's fetch itself (one array): consecutive portions follow each other
+    // in memory, separated only by the rating the conversion loop dropped (quirk Q2).  Such a portion extends the
+    // previous DMA segment; the few entries in between travel along and are never addressed.
+    const int64_t gap = (direct && last && last->direct) ? (int64_t)(indx - (last->indx + last->n)) : -1;
+    if (gap >= 0 && gap <= 64 && (int64_t)(vals - (last->vals + last->n)) == gap && last->dev_off + last->n == base &&
+        region_pinned(c, last->indx, (size_t)(last->n + gap + off) * 4) &&
+        region_pinned(c, last->vals, (size_t)(last->n + gap + off) * 4)) {
+      last->n += gap + off;
+      if (gap) {
+        for (size_t r = 0; r < n_added; ++r) b.start[r0 + r] += gap;
+        run += gap;
+      }
+    } else if (!direct && last && !last->direct) {
+      last->n += off;                                           // staged segments are adjacent by construction
+    } else {
+      b.segs.push_back({indx, vals, off, base, b.staged, direct});
+    }
+    if (!direct) {
+      const size_t cap = (size_t)(c->batch_flush_ratings + kBatchDirectRatings);
+      char* h = (char*)b.slot->host;
+      memcpy(h + (size_t)b.staged * 4, indx, (size_t)off * 4);
+      memcpy(h + cap * 4 + (size_t)b.staged * 4, vals, (size_t)off * 4);
+      b.staged += off;
+    }
+  }
+  b.ratings = run;
+  const int32_t first = R > 0 ? rows[1] : -1, lastr = R > 0 ? rows[1 + 2 * (size_t)(R - 1)] : -1;
+  if (kind == 1 && R > 0) b.ranges.emplace_back(first, lastr);
+  if (info) {
+    memset(info, 0, sizeof(*info));
+    info->rows_from = first;
+    info->rows_cnt = R;
+    info->ratings_in_portion = off;
+  }
+  if (kind == 2) {
+    ycnr_portion_info pi;
+    memset(&pi, 0, sizeof(pi));
+    pi.rows_from = first;
+    pi.rows_cnt = R;
+    pi.ratings_in_portion = off;
+    b.tags.push_back(tag);
+    b.infos.push_back(pi);
+  }
+  c->t_portions++;
+  if (b.ratings >= c->batch_flush_ratings) OK(batch_flush(c));
+  return 0;
+}
+
+int batch_flush(ycnr_ctx* c) {
+  Batch& b = c->batch;
+  if (b.kind == 0) return 0;
+  const int kind = b.kind;
+  b.kind = 0;
+  Slot& sl = *b.slot;
+  const int R = (int)b.n_rows;
+  const int P = (int)b.tags.size();
+  const int64_t off = b.ratings;
+  c->max_batch_rows = std::max(c->max_batch_rows, b.n_rows);
+  const double tp0 = now_ms();
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  DevPlan plan;
+  const PlanCfg cfg{c->dual_max, c->split_cols, c->fused_max};
+  if (kind == 1) plan_count(b.len, 1, R, cfg, plan);
+  const size_t pw = kind == 1 ? plan.words : 0;
+  // device: start[R] i64 | ids[R] | len[R] | pfirst[P+1] | plan | indx | vals | rmse sums
+  // host3 (page-locked): pfirst | plan, then (RMSE) the landing area of the portion sums
+  size_t o_start = 0;
+  size_t o_ids = al(o_start + (size_t)R * 8);
+  size_t o_len = al(o_ids + (size_t)R * 4);
+  size_t o_pf = al(o_len + (size_t)R * 4);
+  size_t o_plan = al(o_pf + (size_t)(P + 2) * 4);
+  size_t o_hdr_end = al(o_plan + pw * 4);
+  size_t o_indx = o_hdr_end;
+  size_t o_vals = al(o_indx + (size_t)off * 4);
+  size_t o_sums = al(o_vals + (size_t)off * 4);
+  size_t total = kind == 2 ? al(o_sums + ((size_t)3 * R + 4 * (size_t)P + 8) * 8) : o_sums;
+  const size_t h3_bytes = o_hdr_end - o_pf, h3_sums = al(h3_bytes);
+  c->max_host3 = std::max(c->max_host3, h3_sums + (size_t)(4 * P + 4) * 8);
+  OK(ensure_pinned(&sl.host3, &sl.host3_cap, c->max_host3));   // (page-locked allocations cost milliseconds: grow all slots once)
+  c->max_slot_dev = std::max(c->max_slot_dev, total);
+  OK(sl.dev.ensure(c->max_slot_dev));
+  char* h3 = (char*)sl.host3;
+  char* d = (char*)sl.dev.p;
+  memset(h3, 0, (size_t)(P + 2) * 4);
+  if (kind == 2) {
+    memcpy(h3, b.pfirst.data(), (size_t)P * 4);
+    ((int32_t*)h3)[P] = R;
+    // (entries stay in portion order here: sorting ~1.7 M validate rows per pass on the host costs more than the
+    //  kernel gains from it)
+  } else {
+    plan_fill(b.len, 1, R, cfg, plan, (int32_t*)(h3 + (o_plan - o_pf)), c->opts.solve_chunks);
+  }
+  const double tp1 = now_ms();
+  c->t_parse += tp1 - tp0;
+  if (R) {
+    CU(cudaMemcpyAsync(d + o_start, b.start, (size_t)R * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(d + o_ids, b.ids, (size_t)R * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(d + o_len, b.len, (size_t)R * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  CU(cudaMemcpyAsync(d + o_pf, h3, h3_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  const size_t cap = (size_t)(c->batch_flush_ratings + kBatchDirectRatings);
+  for (const BatchSeg& sg : b.segs) {
+    const void* si = sg.direct ? (const void*)sg.indx : (const void*)((char*)sl.host + (size_t)sg.stage_off * 4);
+    const void* sv = sg.direct ? (const void*)sg.vals : (const void*)((char*)sl.host + cap * 4 + (size_t)sg.stage_off * 4);
+    CU(cudaMemcpyAsync(d + o_indx + (size_t)sg.dev_off * 4, si, (size_t)sg.n * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(d + o_vals + (size_t)sg.dev_off * 4, sv, (size_t)sg.n * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  CU(cudaEventRecord(c->copied, c->copy_stream));
+  CU(cudaStreamWaitEvent(c->stream, c->copied, 0));
+  c->t_copy_issue += now_ms() - tp1;
+  RowsView view{};
+  view.row_start = (const int64_t*)(d + o_start);
+  view.row_ids = (const int32_t*)(d + o_ids);
+  view.row_len = (const int32_t*)(d + o_len);
+  view.indx = (const int32_t*)(d + o_indx);
+  view.vals = (const float*)(d + o_vals);
+  view.guard = c->d_bad;
+  if (kind == 1) {
+    const int solved = c->step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
+    OK(launch_validate_cols(c, view.indx, off, c->fac_rows[1 - solved]));
+    if (R > 0) {
+      const double tl0 = now_ms();
+      OK(run_als(c, c->step_type, view, plan, (const int32_t*)(d + o_plan), true));
+      c->t_launch += now_ms() - tl0;
+      if (c->h_fac[solved] && c->h_registered[solved]) {
+        // solved rows back to the host segment under the next batch's kernels; portions whose id ranges touch
+        // are copied as one range (rows between two ranges may belong to another worker and are left alone)
+        CU(cudaEventRecord(sl.solved, c->stream));
+        CU(cudaStreamWaitEvent(c->d2h_stream, sl.solved, 0));
+        size_t i = 0;
+        while (i < b.ranges.size()) {
+          int32_t lo = b.ranges[i].first, hi = b.ranges[i].second;
+          size_t j = i + 1;
+          while (j < b.ranges.size() && b.ranges[j].first == hi + 1) { hi = b.ranges[j].second; ++j; }
+          const size_t fo = (size_t)lo * c->k;
+          CU(cudaMemcpyAsync(c->h_fac[solved] + fo, c->d_fac[solved] + fo, (size_t)(hi - lo + 1) * c->k * sizeof(float),
+                             cudaMemcpyDeviceToHost, c->d2h_stream));
+          i = j;
+        }
+        c->d2h_pending = true;
+      } else {
+        for (auto& r : b.ranges) c->solved_ranges.push_back(r);
+      }
+    }
+    OK(finish_slot(c, &sl));
+  } else {
+    OK(launch_validate_cols(c, view.indx, off, c->fac_rows[YCNR_ITEM_FACTORS]));
+    double* d_rows = (double*)(d + o_sums);
+    double* d_port = d_rows + 3 * (size_t)R;
+    if (R > 0) {
+      OK(run_rmse(c, view, R, off, c->rmse_shift, d_rows, (const int32_t*)(d + o_pf), P, d_port));
+    } else {
+      CU(cudaMemsetAsync(d_port, 0, sizeof(double) * 4 * P, c->stream));
+    }
+    CU(cudaMemcpyAsync(h3 + h3_sums, d_port, sizeof(double) * 4 * P, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_bad, c->d_bad, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    OK(finish_slot(c, &sl));
+    int idx = -1;
+    for (size_t i = 0; i < c->rmse_inflight.size(); ++i)
+      if (!c->rmse_inflight[i].live) { idx = (int)i; break; }
+    if (idx < 0) { c->rmse_inflight.emplace_back(); idx = (int)c->rmse_inflight.size() - 1; }
+    RmseInflight& f = c->rmse_inflight[idx];
+    f.slot = &sl;
+    f.done = sl.done;
+    f.tags = b.tags;
+    f.infos = b.infos;
+    f.h_sums = (const double*)(h3 + h3_sums);
+    f.live = true;
+    sl.inflight = idx;
+    c->rmse_order.push_back(idx);
+  }
+  return 0;
+}
+
+// Completed RMSE portions, oldest first.  wait: also flush the open batch and wait for everything in flight.
+int rmse_collect(ycnr_ctx* c, bool wait) {
+  if (wait) OK(batch_flush(c));
+  while (!c->rmse_order.empty()) {
+    const int idx = c->rmse_order.front();
+    OK(drain_inflight(c, idx, wait));
+    if (c->rmse_inflight[idx].live) break;      // not finished yet (and we do not wait): keep the order
+    c->rmse_order.erase(c->rmse_order.begin());
+  }
+  return 0;
+}
+
 void collect_profile(ycnr_ctx* c) {
   for (auto& r : c->prof_open) {
     float ms = 0.f;
@@ -1172,6 +1657,7 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   if (use_tc && c->k > 124 && c->opts.solve_chunks < 2) c->opts.solve_chunks = kMaxChunks;
   c->num_sms = prop.multiProcessorCount;
   c->trace = getenv("YCNR_TRACE") != nullptr;
+  if (const char* e = getenv("YCNR_BATCH_FLUSH")) c->batch_flush_ratings = std::max<int64_t>(1, atoll(e));
   if (const char* e = getenv("YCNR_SPREAD_BULK")) c->spread_bulk = atoi(e) ? 1 : 0;
   c->fac_rows[0] = o->total_users;
   c->fac_rows[1] = o->total_items;
@@ -1211,12 +1697,14 @@ int ycnr_destroy(ycnr_ctx* c) {
     if (c->d_fac[w]) cudaFree(c->d_fac[w]);
   }
   for (auto& rs : c->rowsets) {
-    rs.rows.release(); rs.ratings.release(); rs.plan.release(); rs.sums.release();
+    rs.rows.release(); rs.ratings.release(); rs.plan.release(); rs.sums.release(); rs.order.release(); rs.erows.release();
     if (rs.h_sums) cudaFreeHost(rs.h_sums);
     if (rs.sums_ready) cudaEventDestroy(rs.sums_ready);
   }
   for (auto& s : c->slots) {
     if (s.host) cudaFreeHost(s.host);
+    if (s.host2) cudaFreeHost(s.host2);
+    if (s.host3) cudaFreeHost(s.host3);
     s.dev.release();
     if (s.done) cudaEventDestroy(s.done);
     if (s.solved) cudaEventDestroy(s.solved);
@@ -1341,6 +1829,7 @@ int ycnr_host_unregister(ycnr_ctx* c, void* ptr) {
 int ycnr_start_train_step(ycnr_ctx* c, int32_t step_type) {
   if (!c || (step_type != YCNR_BY_USER && step_type != YCNR_BY_ITEM)) return fail("ycnr_start_train_step: bad stepType");
   OK(set_device(c));
+  OK(rmse_collect(c, true));   // (nothing is left queued from an earlier pass)
   c->step_type = step_type;
   c->solved_ranges.clear();
   const int solved = step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
@@ -1357,6 +1846,17 @@ int ycnr_als_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, cons
     return fail("ycnr_als_portion: call ycnr_start_train_step first");
   const double t0 = now_ms();
   OK(set_device(c));
+  if (rows[0] >= 0 && rows[0] < (1 << 20)) {   // small portions are queued and launched in batches
+    int64_t off = 0;
+    const int solved_w = c->step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
+    OK(check_header(rows, rows[0], c->fac_rows[solved_w], &off));
+    if (off < kBatchDirectRatings) {
+      OK(batch_add(c, 1, rows, indx, vals, off, 0, info));
+      if (info) info->time_ms = now_ms() - t0;
+      return 0;
+    }
+  }
+  OK(batch_flush(c));
   StagedPortion s;
   OK(stage_portion(c, rows, indx, vals, s));
   if (s.n_rows > 0) {
@@ -1393,6 +1893,7 @@ int ycnr_end_train_step(ycnr_ctx* c) {
   if (!c) return fail("ycnr_end_train_step: null context");
   if (c->step_type != YCNR_BY_USER && c->step_type != YCNR_BY_ITEM) return fail("ycnr_end_train_step: no step open");
   OK(set_device(c));
+  OK(batch_flush(c));
   const int solved = c->step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
   if (c->h_fac[solved]) {
     // merge the per-portion [first,last] ranges (ascending in practice) and copy them back
@@ -1439,20 +1940,36 @@ int ycnr_end_train_step(ycnr_ctx* c) {
 int ycnr_start_calc_rmse(ycnr_ctx* c, int32_t step_type, double shift) {
   if (!c || (step_type != YCNR_RMSE_VALIDATE && step_type != YCNR_RMSE_TEST)) return fail("ycnr_start_calc_rmse: bad stepType");
   OK(set_device(c));
+  OK(rmse_collect(c, true));   // a queued batch still belongs to the previous pass (its shift)
   c->step_type = step_type;
   c->rmse_shift = shift;
   OK(ensure_fixed_current(c, YCNR_USER_FACTORS));
   OK(ensure_fixed_current(c, YCNR_ITEM_FACTORS));
+  if (!c->rmse_cur.sums.empty()) std::swap(c->rmse_prev, c->rmse_cur);
+  c->rmse_cur.sums.clear();
+  c->rmse_cur.step_type = step_type;
+  c->rmse_cur.shift = shift;
+  c->rmse_cur.ver[0] = c->fac_version[0];
+  c->rmse_cur.ver[1] = c->fac_version[1];
   return 0;
 }
 
+static int rmse_portion_sync(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals, ycnr_portion_info* info,
+                             double* ratings_sum_out);
+
 int ycnr_rmse_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals,
                       ycnr_portion_info* info) {
+  return rmse_portion_sync(c, rows, indx, vals, info, nullptr);
+}
+
+static int rmse_portion_sync(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals, ycnr_portion_info* info,
+                             double* ratings_sum_out) {
   if (!c || !rows || !indx || !vals || !info) return fail("ycnr_rmse_portion: null argument");
   if (c->step_type != YCNR_RMSE_VALIDATE && c->step_type != YCNR_RMSE_TEST)
     return fail("ycnr_rmse_portion: call ycnr_start_calc_rmse first");
   const double t0 = now_ms();
   OK(set_device(c));
+  OK(rmse_collect(c, true));
   StagedPortion s;
   OK(stage_rmse_portion(c, rows, indx, vals, s));
   double sums[4] = {0, 0, 0, 0};
@@ -1477,6 +1994,90 @@ int ycnr_rmse_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, con
   info->r_cnt = sums[1];
   info->r_sum = sums[2];
   info->time_ms = now_ms() - t0;
+  if (ratings_sum_out) *ratings_sum_out = sums[3];
+  return 0;
+}
+
+int ycnr_rmse_portion_async(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals, int64_t tag) {
+  if (!c || !rows || !indx || !vals) return fail("ycnr_rmse_portion_async: null argument");
+  if (c->step_type != YCNR_RMSE_VALIDATE && c->step_type != YCNR_RMSE_TEST)
+    return fail("ycnr_rmse_portion_async: call ycnr_start_calc_rmse first");
+  OK(set_device(c));
+  {   // the same portion of the same set under the previous shift, factors untouched: derive (see rmse_prev)
+    const auto& pv = c->rmse_prev;
+    if (pv.step_type == c->step_type && pv.ver[0] == c->fac_version[0] && pv.ver[1] == c->fac_version[1] &&
+        c->batch.kind == 0 && c->rmse_order.empty()) {
+      auto it = pv.sums.find(tag);
+      const int R = rows[0];
+      if (it != pv.sums.end() && it->second.rows_cnt == R && (R == 0 || it->second.rows_from == rows[1])) {
+        const auto& q = it->second;
+        const double d = c->rmse_shift - pv.shift;
+        ycnr_portion_info pi;
+        memset(&pi, 0, sizeof(pi));
+        pi.rows_from = q.rows_from;
+        pi.rows_cnt = q.rows_cnt;
+        pi.ratings_in_portion = q.ratings;
+        pi.r_sum_diff2 = q.d2 - 2.0 * d * (q.rat - q.pred) + q.cnt * d * d;
+        pi.r_cnt = q.cnt;
+        pi.r_sum = q.pred + q.cnt * d;
+        c->rmse_done.emplace_back(tag, pi);
+        c->rmse_cur.sums[tag] = {q.rows_from, q.rows_cnt, q.ratings, pi.r_sum_diff2, q.cnt, pi.r_sum, q.rat};
+        return 0;
+      }
+    }
+  }
+  if (rows[0] >= 0 && rows[0] < (1 << 20)) {
+    int64_t off = 0;
+    OK(check_header(rows, rows[0], c->fac_rows[YCNR_USER_FACTORS], &off));
+    if (off < kBatchDirectRatings) return batch_add(c, 2, rows, indx, vals, off, tag, nullptr);
+  }
+  ycnr_portion_info pi;
+  double rat = 0.0;
+  OK(rmse_portion_sync(c, rows, indx, vals, &pi, &rat));     // large portion: the single-portion path, synchronous
+  c->rmse_done.emplace_back(tag, pi);
+  c->rmse_cur.sums[tag] = {pi.rows_from, pi.rows_cnt, pi.ratings_in_portion, pi.r_sum_diff2, pi.r_cnt, pi.r_sum, rat};
+  return 0;
+}
+
+int ycnr_rmse_poll(ycnr_ctx* c, int32_t wait, int32_t max_out, int64_t* tags_out, ycnr_portion_info* infos_out,
+                   int32_t* n_out) {
+  if (!c || !n_out || max_out < 0 || (max_out && (!tags_out || !infos_out))) return fail("ycnr_rmse_poll: bad argument");
+  OK(set_device(c));
+  *n_out = 0;
+  OK(rmse_collect(c, wait != 0));
+  if (*c->h_bad) {
+    *c->h_bad = 0;
+    CU(cudaMemset(c->d_bad, 0, sizeof(int32_t)));
+    return fail("ycnr_rmse_portion: item id outside the item factor matrix (0..%lld)", (long long)c->fac_rows[1] - 1);
+  }
+  int n = 0;
+  while (n < max_out && c->rmse_done_head < c->rmse_done.size()) {
+    tags_out[n] = c->rmse_done[c->rmse_done_head].first;
+    infos_out[n] = c->rmse_done[c->rmse_done_head].second;
+    ++c->rmse_done_head;
+    ++n;
+  }
+  if (c->rmse_done_head == c->rmse_done.size()) {
+    c->rmse_done.clear();
+    c->rmse_done_head = 0;
+  }
+  *n_out = n;
+  return 0;
+}
+
+// n calls of ycnr_als_portion / ycnr_rmse_portion_async issued from native code (a binding whose per-call overhead
+// matters — a Python loop spends ~10 us per message — hands over the pointers of n filled portion buffers).
+int ycnr_als_portions(ycnr_ctx* c, int32_t n, const int32_t* const* rows, const int32_t* const* indx,
+                      const float* const* vals, ycnr_portion_info* infos) {
+  if (!c || n < 0 || (n && (!rows || !indx || !vals))) return fail("ycnr_als_portions: bad argument");
+  for (int i = 0; i < n; ++i) OK(ycnr_als_portion(c, rows[i], indx[i], vals[i], infos ? infos + i : nullptr));
+  return 0;
+}
+
+int ycnr_rmse_portions_async(ycnr_ctx* c, int32_t n, const int32_t* const* rows, const int32_t* const* indx,
+                             const float* const* vals, const int64_t* tags) {
+  if (!c || n < 0 || (n && (!rows || !indx || !vals))) return fail("ycnr_rmse_portions_async: bad argument");
+  for (int i = 0; i < n; ++i) OK(ycnr_rmse_portion_async(c, rows[i], indx[i], vals[i], tags ? tags[i] : i));
   return 0;
 }
 
@@ -1636,7 +2237,7 @@ int ycnr_rowset_create(ycnr_ctx* c, int32_t step_type, int32_t n_rows, const int
     OK(rs.plan.ensure(packed.size() * 4));
     CU(cudaMemcpyAsync(rs.plan.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, c->stream));
   } else {
-    OK(rs.sums.ensure(((size_t)3 * n_rows + 4 * (size_t)n_portions + 4) * sizeof(double)));
+    OK(build_rmse_entries(c, rs, row_ids, row_start, row_len, portion_first));
   }
   CU(cudaStreamSynchronize(c->stream));  // host sources may be freed by the caller on return
   *out = id;
@@ -1648,7 +2249,7 @@ int ycnr_rowset_destroy(ycnr_ctx* c, int32_t id) {
   OK(set_device(c));
   CU(cudaStreamSynchronize(c->stream));
   RowSet& rs = c->rowsets[id];
-  rs.rows.release(); rs.ratings.release(); rs.plan.release(); rs.sums.release();
+  rs.rows.release(); rs.ratings.release(); rs.plan.release(); rs.sums.release(); rs.order.release(); rs.erows.release();
   if (rs.h_sums) cudaFreeHost(rs.h_sums);
   if (rs.sums_ready) cudaEventDestroy(rs.sums_ready);
   rs.h_sums = nullptr;
@@ -1691,8 +2292,9 @@ int ycnr_rmse_rowset_begin(ycnr_ctx* c, int32_t id, double shift) {
   if (!rs.h_sums) CU(cudaMallocHost(&rs.h_sums, sizeof(double) * 4 * rs.n_portions));
   if (!rs.sums_ready) CU(cudaEventCreateWithFlags(&rs.sums_ready, cudaEventDisableTiming));
   double* d_rows = (double*)rs.sums.p;
-  double* d_port = d_rows + 3 * (size_t)rs.n_rows;
-  OK(run_rmse(c, rs.view, rs.n_rows, rs.nnz, shift, d_rows, rs.d_portion_first, rs.n_portions, d_port));
+  double* d_port = d_rows + 3 * (size_t)rs.n_entries;
+  OK(run_rmse(c, rs.eview, rs.n_entries, rs.nnz, shift, d_rows, rs.d_efirst, rs.n_portions, d_port, nullptr,
+              (const int32_t*)rs.order.p));
   CU(cudaMemcpyAsync(rs.h_sums, d_port, sizeof(double) * 4 * rs.n_portions, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaEventRecord(rs.sums_ready, c->stream));
   rs.pending = true;
@@ -1732,6 +2334,25 @@ int ycnr_rmse_rowset(ycnr_ctx* c, int32_t id, double shift, double* totals, doub
     totals[1] += q[1];
     totals[2] += sp;
   }
+  return 0;
+}
+
+// Sum of the ratings themselves over the row set and over its last portion (from the sums of the last pass):
+// with them a host layer that has gathered the pass at shift 0 from all ranks derives the pass at any other shift.
+int ycnr_rmse_rowset_ratings(ycnr_ctx* c, int32_t id, double* total_out, double* last_portion_out) {
+  if (!c || !total_out || id < 0 || id >= (int)c->rowsets.size() || !c->rowsets[id].used) return fail("ycnr_rmse_rowset_ratings: bad argument");
+  RowSet& rs = c->rowsets[id];
+  *total_out = 0.0;
+  if (last_portion_out) *last_portion_out = 0.0;
+  if (rs.n_rows == 0) return 0;
+  if (rs.pending) {
+    CU(cudaEventSynchronize(rs.sums_ready));
+    rs.pending = false;
+    rs.cached = true;
+  }
+  if (!rs.cached) return fail("ycnr_rmse_rowset_ratings: no RMSE pass has run on this row set yet");
+  for (int p = 0; p < rs.n_portions; ++p) *total_out += rs.h_sums[4 * (size_t)p + 3];
+  if (last_portion_out) *last_portion_out = rs.h_sums[4 * (size_t)(rs.n_portions - 1) + 3];
   return 0;
 }
 
@@ -2007,7 +2628,15 @@ int ycnr_rowset_from_table(ycnr_ctx* c, int32_t step_type, uint32_t set_mask, in
     CU(cudaMemcpyAsync(rs.plan.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   } else {
-    OK(rs.sums.ensure(((size_t)3 * n_rows + 4 * (size_t)P + 4) * sizeof(double)));
+    std::vector<int32_t> h_ids((size_t)std::max(n_rows, 1)), h_pf((size_t)P + 1);
+    std::vector<int64_t> h_start((size_t)std::max(n_rows, 1));
+    if (n_rows) {
+      CU(cudaMemcpyAsync(h_ids.data(), d + o_ids, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaMemcpyAsync(h_start.data(), d, (size_t)n_rows * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaMemcpyAsync(h_pf.data(), d + o_pf, (size_t)(P + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    OK(build_rmse_entries(c, rs, h_ids.data(), h_start.data(), h_len.data(), h_pf.data()));
   }
   *out = id;
   return 0;

@@ -35,6 +35,25 @@ def balanced_cuts(ends, world):
     return cuts
 
 
+def row_cost(n, k, dual_max=96):
+    """Estimated device time of one solved row with n ratings (arbitrary units: ns on one B200 at k = 100),
+    fitted to the measured per-class times: rows of up to dual_max ratings solve the n x n dual
+    system (gather + Gram ~ n k, factorisation ~ n^3), longer rows pay the tensor-core Gram per rating plus one
+    k x k factorisation — SURVEY.md §8(e): balance on n k^2 + k^3 / 3 rather than on raw nnz when rows are short."""
+    n = np.asarray(n, np.float64)
+    s = k / 100.0
+    dual = 2.0 + 0.20 * s * n + 8.5e-5 * n ** 3
+    primal = 46.0 * s ** 3 + 0.107 * s * s * n
+    return np.where(n <= 0, 0.0, np.where(n <= dual_max, dual, primal))
+
+
+def cost_ends(row_counts, portions_row_id_to, k, dual_max=96):
+    """Cumulative row_cost at every portion end (int64, for balanced_cuts)."""
+    c = np.cumsum(row_cost(row_counts, k, dual_max))
+    pto = np.asarray(portions_row_id_to, np.int64)
+    return np.round(c[pto - 1] * 16.0).astype(np.int64) if len(pto) else np.zeros(0, np.int64)
+
+
 def init_from_env(backend=None):
     """torchrun contract: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT."""
     import torch
@@ -155,6 +174,39 @@ def node_shared_matrices(tag, shapes, rank, init_fn=None, group=None):
 def barrier(group=None):
     import torch.distributed as dist
     dist.barrier(group=group)
+
+
+_stream_cache = {}
+
+
+def stream_barrier(ctx, group=None):
+    """Device-side barrier on the library stream: a one-element NCCL all-reduce enqueued behind everything the
+    context has launched; the stream continues when every rank has got there.  The host does not wait, so it
+    queues the next half-step while the barrier is in flight (a host synchronize + dist.barrier() pair cost
+    two host round trips per half-step)."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.cuda.current_device()
+    key = (id(ctx), dev)
+    if key not in _stream_cache:
+        _stream_cache.clear()
+        _stream_cache[key] = (torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", dev)),
+                              torch.zeros(1, device=torch.device("cuda", dev)))
+    st, t = _stream_cache[key]
+    with torch.cuda.stream(st):
+        dist.all_reduce(t, group=group)
+
+
+def all_gather_doubles(values, group=None):
+    """Every rank's list of doubles, in rank order (one all-gather; device tensors under NCCL, CPU under gloo)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.tensor([float(v) for v in values], dtype=torch.float64, device=dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return torch.stack(parts).cpu().tolist()
 
 
 def reduce_rmse(sums, last, group=None):

@@ -57,6 +57,9 @@ class EmfMaster(EmfBase):
         self._ranges = {}
         self.phase_ms = {}
         self._workerMU = []
+        self._prepared = {}
+        self._rmseGlobal = {}
+        self._alsSteps = 0
 
     # ---- prepare ---------------------------------------------------------------------------
     def splitDataForTrain(self):
@@ -101,7 +104,10 @@ class EmfMaster(EmfBase):
         if self.world == 1 or n == 0:
             return 0, n
         ptr = self._csr(step).ptr
-        ends = ptr[np.asarray(pto, np.int64)]            # cumulative ratings at each portion end
+        if step in ("byUser", "byItem"):                 # estimated solve cost per row, not raw nnz
+            ends = ydist.cost_ends(np.diff(ptr), pto, self.factorsCount)
+        else:
+            ends = ptr[np.asarray(pto, np.int64)]        # cumulative ratings at each portion end
         cuts = ydist.balanced_cuts(ends, self.world)
         return int(cuts[self.rank]), int(cuts[self.rank + 1])
 
@@ -184,6 +190,16 @@ class EmfMaster(EmfBase):
                              "fetched": int(csr.ptr[pto[p]]) - a})
             self.portionCache[step] = bufs
 
+    def _preparedPortions(self, step, prefix, lo, hi):
+        key = (step, lo, hi)
+        if key not in self._prepared:
+            bufs = self.portionCache[step][lo:hi]
+            prep = self.ctx.prepare_portions([(b[prefix + "Rows"], b[prefix + "Indx"], b[prefix + "Vals"]) for b in bufs],
+                                             tags=list(range(lo, hi)))
+            prep["h2d"] = sum(8 * b["fetched"] + 4 * len(b[prefix + "Rows"]) for b in bufs)
+            self._prepared[key] = prep
+        return self._prepared[key]
+
     def prepareBulkOnDevice(self):
         """gpu.deviceIngest: upload the ratings table once and let the device build every step's fetch and
         portion headers (ycnr_table_upload / ycnr_rowset_from_table) — the master's SQL fetch + per-rating
@@ -196,7 +212,10 @@ class EmfMaster(EmfBase):
                 self.my_portions[step] = (0, len(pto))
             else:                                                # nnz-balanced contiguous slice, from the device counts
                 cnt = self.ctx.table_counts(STEP_MASK[step], step == "byItem")
-                ends = np.cumsum(cnt, dtype=np.int64)[pto.astype(np.int64) - 1]
+                if step in ("byUser", "byItem"):
+                    ends = ydist.cost_ends(cnt, pto, self.factorsCount)
+                else:
+                    ends = np.cumsum(cnt, dtype=np.int64)[pto.astype(np.int64) - 1]
                 cuts = ydist.balanced_cuts(ends, self.world)
                 self.my_portions[step] = (int(cuts[self.rank]), int(cuts[self.rank + 1]))
             lo, hi = self.my_portions[step]                      # this rank's contiguous slice of the plan
@@ -251,6 +270,9 @@ class EmfMaster(EmfBase):
         worker]; the workers answer 'getMemoryUsage' with 'setMemoryUsage' (EmfWorker.js:43,109-113)."""
         import resource
         self._workerMU = []
+        self._prepared = {}
+        self._rmseGlobal = {}
+        self._alsSteps = 0
         for w in self.workers:
             w.master_side.emit("getMemoryUsage")
         shm = sum(int(a.nbytes) for a in (self.userFactors, self.itemFactors) if a is not None)
@@ -273,6 +295,7 @@ class EmfMaster(EmfBase):
 
     def alsTrainStep(self, stepType):
         """EmfLord.alsTrainStep (EmfLord.js:963-984)."""
+        self._alsSteps += 1
         mp = self.workers[0].master_side
         if self.options["gpu"]["bulk"]:
             self.ctx.als_rowset(self.rowsets[stepType])
@@ -284,6 +307,14 @@ class EmfMaster(EmfBase):
             self.completedPortions = 0
             mp.emit("startTrainStep", {"stepType": stepType})
             cache = getattr(self, "portionCache", None)
+            if cache is not None and self.options["gpu"].get("nativeLoop", False):
+                # the per-portion calls of the whole half-step issued by native code (ycnr_als_portions): what an
+                # N-API binding costs per message is microseconds, a Python message round trip is ~20 us
+                prep = self._preparedPortions(stepType, "als", lo, hi)
+                self.ctx.als_portions(prep)
+                self.completedPortions += prep["n"]
+                self.h2d_bytes += prep["h2d"]
+                lo = hi
             for p in range(lo, hi):
                 if cache is not None:
                     cb = cache[stepType][p]
@@ -310,9 +341,14 @@ class EmfMaster(EmfBase):
 
     def _refresh_replicas(self, stepType):
         which = native.USER_FACTORS if stepType == "byUser" else native.ITEM_FACTORS
-        if self.fusedPeers and (self.options["gpu"]["bulk"] or self.sharedHost):
-            self.ctx.synchronize()          # my peer stores are complete ...
-            ydist.barrier(self.group)       # ... and so are everybody else's into my replica
+        if self.fusedPeers and self.options["gpu"]["bulk"]:
+            # my peer stores are complete when my kernels are, everybody else's into my replica when theirs are:
+            # a barrier in stream order, the host moves on
+            ydist.stream_barrier(self.ctx, self.group)
+            return
+        if self.fusedPeers and self.sharedHost:
+            self.ctx.synchronize()
+            ydist.barrier(self.group)
             return
         if stepType not in self._ranges:    # static per step: the portion plan does not change between iterations
             self._ranges[stepType] = ydist.all_ranges(self._solved_range(stepType), self.world, self.group)
@@ -338,6 +374,33 @@ class EmfMaster(EmfBase):
             self.rSum += msg["rSum"]
             self._lastRmseMsg = msg
 
+    def _gatherRmseShift0(self):
+        """world > 1, bulk: 'rmseSaveCalcs' (EmfMaster.js:726-736) for the validate AND the test pass in one
+        all-gather — sums at shift 0 plus the sum of the ratings, with which every rank derives the pass at any
+        other shift (the third pass) without another exchange."""
+        d = self.options["dataSetDistr"]
+        vec = []
+        for step, pct in (("rmseValidate", d[1]), ("rmseTest", d[2])):
+            lo, hi = self.my_portions[step]
+            if pct and hi > lo:
+                tot, ps = self.ctx.rmse_rowset(self.rowsets[step], 0.0, hi - lo)
+                rsum, rlast = self.ctx.rmse_rowset_ratings(self.rowsets[step])
+                vec += [tot[0], tot[1], tot[2], rsum, ps[-1, 2], ps[-1, 1], 1.0]
+            else:
+                vec += [0.0] * 7
+        rows = ydist.all_gather_doubles(vec, self.group)
+        for si, step in enumerate(("rmseValidate", "rmseTest")):
+            g = {"D": 0.0, "C": 0.0, "P": 0.0, "R": 0.0, "lastP": 0.0, "lastC": 0.0, "ver": self._alsSteps}
+            for r in rows:                               # rank order: deterministic sums; last portion = highest rank
+                v = r[7 * si:7 * si + 7]
+                g["D"] += v[0]
+                g["C"] += v[1]
+                g["P"] += v[2]
+                g["R"] += v[3]
+                if v[6] != 0.0:
+                    g["lastP"], g["lastC"] = v[4], v[5]
+            self._rmseGlobal[step] = g
+
     def calcRmse(self, stepType, useGlobalAvgShift):
         """EmfLord.calcRmse (EmfLord.js:1043-1081) + EmfMaster._startCalcRmse (389-412)."""
         d = self.options["dataSetDistr"]
@@ -346,6 +409,16 @@ class EmfMaster(EmfBase):
         calcGlobalAvgShift = not useGlobalAvgShift
         if calcGlobalAvgShift:
             self.globalAvgShift = 0.0
+        g = self._rmseGlobal.get(stepType)
+        if self.world > 1 and self.options["gpu"]["bulk"] and g and g["ver"] == self._alsSteps:
+            s_ = self.globalAvgShift                     # every rating's prediction moves by the shift
+            self.rSumDiff2 = g["D"] - 2.0 * s_ * (g["R"] - g["P"]) + g["C"] * s_ * s_
+            self.rCnt, self.rSum = g["C"], g["P"] + g["C"] * s_
+            self.rmse = math.sqrt(self.rSumDiff2 / self.rCnt) if self.rCnt else float("nan")
+            self.predAvg = (g["lastP"] + g["lastC"] * s_) / g["lastC"] if g["lastC"] else float("nan")
+            if calcGlobalAvgShift:
+                self.globalAvgShift = self.stats["totalRatingsAvg"] - self.predAvg
+            return self.rmse
         self.rSum = self.rSumDiff2 = self.rCnt = 0.0
         self._lastRmseMsg = None
         lo, hi = self.my_portions[stepType]
@@ -361,6 +434,15 @@ class EmfMaster(EmfBase):
             pb = self.workers[0].portionBuffer
             mp.emit("startCalcRmse", {"stepType": stepType, "globalAvgShift": self.globalAvgShift})
             cache = getattr(self, "portionCache", None)
+            if cache is not None and self.options["gpu"].get("nativeLoop", False):
+                prep = self._preparedPortions(stepType, "rmse", lo, hi)
+                self.ctx.rmse_portions_async(prep)
+                for tag, info in self.ctx.rmse_poll(True):
+                    self.wm_completedPortion({"portionNo": int(tag), "rSumDiff2": info.r_sum_diff2, "rCnt": info.r_cnt,
+                                              "rSum": info.r_sum})
+                self.h2d_bytes += prep["h2d"]
+                self.d2h_bytes += 24 * prep["n"]
+                lo = hi
             for p in range(lo, hi):
                 if cache is not None:
                     cb = cache[stepType][p]
@@ -373,6 +455,7 @@ class EmfMaster(EmfBase):
                 self.h2d_bytes += 8 * fetched + 4 * (2 * int(pb["rmseRows"][0]) + 1)
                 mp.emit("calcRmsePortion", {"portionNo": p})
                 self.d2h_bytes += 24
+            mp.emit("endCalcRmse")
         last = self._lastRmseMsg
         if self.world > 1:   # 'rmseSaveCalcs' reduce-to-root + the last portion's partials (Q7)
             (self.rSumDiff2, self.rCnt, self.rSum), last = ydist.reduce_rmse(
@@ -407,6 +490,8 @@ class EmfMaster(EmfBase):
                 lo, hi = self.my_portions[step]
                 if pct and hi > lo:
                     self.ctx.rmse_rowset_begin(self.rowsets[step], 0.0)
+            if self.world > 1:
+                self._gatherRmseShift0()
         out = {
             "rmseValidate": self._timed("rmseValidate", self.calcRmse, "rmseValidate", False),
             "rmseTest": self._timed("rmseTest", self.calcRmse, "rmseTest", False),

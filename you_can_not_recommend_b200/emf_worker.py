@@ -57,6 +57,7 @@ class EmfWorker(EmfBase):
         p.on("startTrainStep", self.mw_startTrainStep)
         p.on("endTrainStep", self.mw_endTrainStep)
         p.on("startCalcRmse", self.mw_startCalcRmse)
+        p.on("endCalcRmse", self.mw_endCalcRmse)
         p.on("calcTrainAlsPortion", self.mw_calcTrainAlsPortion)
         p.on("calcTrainSgdPortion", self.mw_calcTrainSgdPortion)
         p.on("calcRmsePortion", self.mw_calcRmsePortion)
@@ -128,19 +129,30 @@ class EmfWorker(EmfBase):
         })
 
     def mw_calcRmsePortion(self, msg):
-        """EmfWorker.mw_calcRmsePortion (EmfWorker.js:266-315)."""
+        """EmfWorker.mw_calcRmsePortion (EmfWorker.js:266-315).  The portion is queued on the GPU (small portions
+        are launched in batches); its 'completedPortion' reply — an asynchronous message upstream as well
+        (EmfWorker.js:304-314) — is emitted as soon as its sums are back, always in portion order."""
         pb = msg.get("portionBuffer") or self.portionBuffer
-        info = self.ctx.rmse_portion(pb["rmseRows"], pb["rmseIndx"], pb["rmseVals"])
-        self.process.emit("completedPortion", {
-            "portionNo": msg["portionNo"],
-            "rowsRange": {"from": info.rows_from if info.rows_cnt > 0 else None, "cnt": info.rows_cnt},
-            "ratingsInPortion": info.ratings_in_portion,
-            "time": info.time_ms,
-            "memoryUsage": None,
-            "rSumDiff2": info.r_sum_diff2,
-            "rCnt": info.r_cnt,
-            "rSum": info.r_sum,
-        })
+        self.ctx.rmse_portion_async(pb["rmseRows"], pb["rmseIndx"], pb["rmseVals"], msg["portionNo"])
+        self._emitCompletedRmse(False)
+
+    def mw_endCalcRmse(self, msg=None):
+        """Addition (like endTrainStep): the master has handed out the last portion of the pass — flush the
+        queue and send the remaining 'completedPortion' replies."""
+        self._emitCompletedRmse(True)
+
+    def _emitCompletedRmse(self, wait):
+        for tag, info in self.ctx.rmse_poll(wait):
+            self.process.emit("completedPortion", {
+                "portionNo": int(tag),
+                "rowsRange": {"from": info.rows_from if info.rows_cnt > 0 else None, "cnt": info.rows_cnt},
+                "ratingsInPortion": info.ratings_in_portion,
+                "time": info.time_ms,
+                "memoryUsage": None,
+                "rSumDiff2": info.r_sum_diff2,
+                "rCnt": info.r_cnt,
+                "rSum": info.r_sum,
+            })
 
     def mw_calcTrainSgdPortion(self, msg):
         raise NotImplementedError("SGD is deprecated upstream (README.md:13) and not on the B200 path")

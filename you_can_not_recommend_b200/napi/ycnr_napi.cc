@@ -195,6 +195,51 @@ napi_value RmsePortion(napi_env env, napi_callback_info info) {
   return portion_result(env, pi, true);
 }
 
+// rmsePortionAsync(handle, rmseRows, rmseIndx, rmseVals, portionNo): queue the portion (small portions are launched
+// in batches); its sums come back from rmsePoll.  The worker's 'completedPortion' replies are asynchronous
+// messages upstream as well (EmfWorker.js:304-314).
+napi_value RmsePortionAsync(napi_env env, napi_callback_info info) {
+  napi_value a[5];
+  ycnr_ctx* c;
+  int32_t *rows, *indx;
+  float* vals;
+  size_t n0, n1, n2;
+  int64_t tag;
+  if (!args(env, info, 5, a) || !handle(env, a[0], &c) || !typed(env, a[1], napi_int32_array, &rows, &n0) ||
+      !typed(env, a[2], napi_int32_array, &indx, &n1) || !typed(env, a[3], napi_float32_array, &vals, &n2) ||
+      napi_get_value_int64(env, a[4], &tag) != napi_ok)
+    return nullptr;
+  if (!check(env, ycnr_check_portion(rows, (int64_t)n0, (int64_t)n1, (int64_t)n2))) return nullptr;
+  check(env, ycnr_rmse_portion_async(c, rows, indx, vals, tag));
+  return undefined(env);
+}
+
+// rmsePoll(handle, wait) -> [{portionNo, rowsFrom, rowsCnt, ratingsInPortion, time, rSumDiff2, rCnt, rSum}, ...] in
+// the order the portions were queued; wait = true flushes the queue and waits for all of them.
+napi_value RmsePoll(napi_env env, napi_callback_info info) {
+  napi_value a[2];
+  ycnr_ctx* c;
+  bool wait = false;
+  if (!args(env, info, 2, a) || !handle(env, a[0], &c) || napi_get_value_bool(env, a[1], &wait) != napi_ok) return nullptr;
+  napi_value arr;
+  napi_create_array(env, &arr);
+  uint32_t out = 0;
+  for (;;) {
+    int64_t tags[256];
+    ycnr_portion_info infos[256];
+    int32_t n = 0;
+    if (!check(env, ycnr_rmse_poll(c, wait ? 1 : 0, 256, tags, infos, &n))) return nullptr;
+    for (int32_t i = 0; i < n; ++i) {
+      napi_value o = portion_result(env, infos[i], true), v;
+      napi_create_int64(env, tags[i], &v);
+      napi_set_named_property(env, o, "portionNo", v);
+      napi_set_element(env, arr, out++, o);
+    }
+    if (n < 256) break;
+  }
+  return arr;
+}
+
 // sAlsBuildSubFixedFacts(sub, fixed, indx, cols, k) — upstream's own signature (cpp_utils/cpp_utils.js:15-19,
 // als_utils.cc:22-38): runs on the process's current context; a 6-argument call with the context handle first
 // is accepted as well.
@@ -422,6 +467,8 @@ napi_value Init(napi_env env, napi_value exports) {
       {"endTrainStep", nullptr, EndTrainStep, nullptr, nullptr, nullptr, 0, nullptr},
       {"startCalcRmse", nullptr, StartCalcRmse, nullptr, nullptr, nullptr, 0, nullptr},
       {"rmsePortion", nullptr, RmsePortion, nullptr, nullptr, nullptr, 0, nullptr},
+      {"rmsePortionAsync", nullptr, RmsePortionAsync, nullptr, nullptr, nullptr, 0, nullptr},
+      {"rmsePoll", nullptr, RmsePoll, nullptr, nullptr, nullptr, 0, nullptr},
       {"sAlsBuildSubFixedFacts", nullptr, SAlsBuildSubFixedFacts, nullptr, nullptr, nullptr, 0, nullptr},
       {"dAlsBuildSubFixedFacts", nullptr, DAlsBuildSubFixedFacts, nullptr, nullptr, nullptr, 0, nullptr},
       {"getMemoryUsage", nullptr, GetMemoryUsage, nullptr, nullptr, nullptr, 0, nullptr},

@@ -22,9 +22,10 @@ EXPORTS = [
     "ycnr_last_error", "ycnr_device_count", "ycnr_create", "ycnr_destroy", "ycnr_attach_factors",
     "ycnr_upload_factors", "ycnr_download_factors", "ycnr_invalidate_device", "ycnr_device_factors",
     "ycnr_stream", "ycnr_synchronize", "ycnr_host_register", "ycnr_host_unregister", "ycnr_start_train_step", "ycnr_als_portion", "ycnr_end_train_step",
-    "ycnr_start_calc_rmse", "ycnr_rmse_portion", "ycnr_s_als_build_sub_fixed_facts", "ycnr_s_als_build_sub_fixed_facts_noctx",
+    "ycnr_start_calc_rmse", "ycnr_rmse_portion", "ycnr_rmse_portion_async", "ycnr_rmse_poll", "ycnr_als_portions",
+    "ycnr_rmse_portions_async", "ycnr_s_als_build_sub_fixed_facts", "ycnr_s_als_build_sub_fixed_facts_noctx",
     "ycnr_check_portion", "ycnr_factor_elems", "ycnr_memory_usage", "ycnr_rowset_create",
-    "ycnr_rowset_destroy", "ycnr_als_rowset", "ycnr_rmse_rowset", "ycnr_rmse_rowset_begin", "ycnr_ipc_export", "ycnr_ipc_import",
+    "ycnr_rowset_destroy", "ycnr_als_rowset", "ycnr_rmse_rowset", "ycnr_rmse_rowset_begin", "ycnr_rmse_rowset_ratings", "ycnr_ipc_export", "ycnr_ipc_import",
     "ycnr_ipc_close", "ycnr_set_peers", "ycnr_table_upload", "ycnr_table_split", "ycnr_table_counts", "ycnr_rowset_from_table",
     "ycnr_rowset_info", "ycnr_rowset_read", "ycnr_recommend_batch", "ycnr_debug_plan", "ycnr_debug_read_partials", "ycnr_profile_reset", "ycnr_profile_read",
     "ycnr_profile_dual_bins",
@@ -203,6 +204,54 @@ class Context:
         _check(lib().ycnr_rmse_portion(self._h, _i32(rows), _i32(indx), _f32(vals), C.byref(info)))
         return info
 
+    def rmse_portion_async(self, rows, indx, vals, tag):
+        """Queue an RMSE portion under `tag`; results come back from rmse_poll in queue order."""
+        _check(lib().ycnr_check_portion(_i32(rows), C.c_int64(len(rows)), C.c_int64(len(indx)), C.c_int64(len(vals))))
+        _check(lib().ycnr_rmse_portion_async(self._h, _i32(rows), _i32(indx), _f32(vals), C.c_int64(tag)))
+
+    def rmse_poll(self, wait=False, max_out=4096):
+        """[(tag, PortionInfo)] of completed RMSE portions, oldest first; wait=True flushes and waits for all."""
+        out = []
+        while True:
+            tags = (C.c_int64 * max_out)()
+            infos = (PortionInfo * max_out)()
+            n = C.c_int32(0)
+            _check(lib().ycnr_rmse_poll(self._h, C.c_int32(int(wait)), C.c_int32(max_out), tags, infos, C.byref(n)))
+            out.extend((tags[i], infos[i]) for i in range(n.value))
+            if n.value < max_out:
+                return out
+
+    @staticmethod
+    def _ptr_array(arrays, ctype):
+        return (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+
+    def prepare_portions(self, portions, tags=None):
+        """Pointer tables for n filled portion buffers [(rows, indx, vals)] (kept alive by the returned object):
+        what a native binding hands to ycnr_als_portions / ycnr_rmse_portions_async."""
+        n = len(portions)
+        for r, i, v in portions:
+            _check(lib().ycnr_check_portion(_i32(r), C.c_int64(len(r)), C.c_int64(len(i)), C.c_int64(len(v))))
+        return {"n": n, "keep": portions,
+                "rows": self._ptr_array([p[0] for p in portions], C.c_int32),
+                "indx": self._ptr_array([p[1] for p in portions], C.c_int32),
+                "vals": self._ptr_array([p[2] for p in portions], C.c_float),
+                "infos": (PortionInfo * max(n, 1))(),
+                "tags": (C.c_int64 * max(n, 1))(*(tags if tags is not None else range(n)))}
+
+    def als_portions(self, prepared):
+        """One ycnr_als_portion call per prepared portion, issued from native code; returns the PortionInfo array."""
+        if not isinstance(prepared, dict):
+            prepared = self.prepare_portions(prepared)
+        _check(lib().ycnr_als_portions(self._h, C.c_int32(prepared["n"]), prepared["rows"], prepared["indx"],
+                                       prepared["vals"], prepared["infos"]))
+        return prepared["infos"]
+
+    def rmse_portions_async(self, prepared):
+        if not isinstance(prepared, dict):
+            prepared = self.prepare_portions(prepared)
+        _check(lib().ycnr_rmse_portions_async(self._h, C.c_int32(prepared["n"]), prepared["rows"], prepared["indx"],
+                                              prepared["vals"], prepared["tags"]))
+
     def build_sub_fixed_facts(self, sub, fixed, indx):
         k = fixed.shape[1]
         _check(lib().ycnr_s_als_build_sub_fixed_facts(self._h, _f32(sub), _f32(fixed), C.c_int64(fixed.shape[0]),
@@ -229,6 +278,11 @@ class Context:
 
     def als_rowset(self, rowset):
         _check(lib().ycnr_als_rowset(self._h, C.c_int32(rowset)))
+
+    def rmse_rowset_ratings(self, rowset):
+        tot, last = C.c_double(0), C.c_double(0)
+        _check(lib().ycnr_rmse_rowset_ratings(self._h, C.c_int32(rowset), C.byref(tot), C.byref(last)))
+        return tot.value, last.value
 
     def rmse_rowset_begin(self, rowset, shift):
         _check(lib().ycnr_rmse_rowset_begin(self._h, C.c_int32(rowset), C.c_double(shift)))
