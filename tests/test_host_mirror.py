@@ -110,14 +110,14 @@ def test_manager_persistence_roundtrip_cpu(tmp_path):
 
 def test_launch_plan_classes_cpu():
     """The library's host-side launch planning (csrc/ycnr_als.cu plan_count / plan_fill), no GPU: rows with
-    n <= 0 are skipped (Q2 degenerate rows), n <= 96 go to the dual bin of their tile-row count ceil(n/4), longer
+    n <= 0 are skipped (Q2 degenerate rows), n <= 88 (k = 100) go to the dual bin of their tile-row count ceil(n/4), longer
     rows are cut into <= 4096-rating slices for the tensor-core Gram, and the slices are handed out longest first."""
     import numpy as np
     from you_can_not_recommend_b200 import native
-    lens = np.asarray([0, 1, 4, 5, 96, 97, 4096, 4097, 10000, -1, 33, 300], np.int32)
+    lens = np.asarray([0, 1, 4, 5, 88, 89, 4096, 4097, 10000, -1, 33, 300], np.int32)
     p = native.debug_plan(lens, factors_count=100)
-    assert [list(b) for b in p["dual"] if len(b)] == [[1, 2], [3], [10], [4]]         # mt = 1, 2, 9, 24
-    assert list(p["dual"][0]) == [1, 2] and list(p["dual"][1]) == [3] and list(p["dual"][8]) == [10] and list(p["dual"][23]) == [4]
+    assert [list(b) for b in p["dual"] if len(b)] == [[1, 2], [3], [10], [4]]         # mt = 1, 2, 9, 22
+    assert list(p["dual"][0]) == [1, 2] and list(p["dual"][1]) == [3] and list(p["dual"][8]) == [10] and list(p["dual"][21]) == [4]
     assert list(p["fused"]) == [] and list(p["multi"]) == [5, 6, 7, 8, 11]
     items = list(zip(p["item_row"].tolist(), p["item_off"].tolist()))
     assert items == [(5, 0), (6, 0), (7, 0), (7, 4096), (8, 0), (8, 4096), (8, 8192), (11, 0)]
@@ -125,6 +125,9 @@ def test_launch_plan_classes_cpu():
     order = p["item_order"].tolist()
     assert sorted(order) == list(range(len(items)))
     assert [slice_len[i] // 32 for i in order] == sorted((l // 32 for l in slice_len), reverse=True)
+    # the measured dual / primal crossover: 88 ratings on the tensor-core path at k = 100, 96 for wide systems
+    assert len(native.debug_plan(np.asarray([96], np.int32), factors_count=100)["multi"]) == 1
+    assert len(native.debug_plan(np.asarray([96], np.int32), factors_count=256)["dual"][23]) == 1
     # FFMA path (k % 4 != 0): rows up to split_cols are fused rows, longest first; k = 7 -> dual rows up to 4 ratings
     q = native.debug_plan(lens, factors_count=7)
     assert list(q["dual"][0]) == [1, 2] and sum(len(b) for b in q["dual"]) == 2

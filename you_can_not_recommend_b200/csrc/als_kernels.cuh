@@ -773,6 +773,68 @@ __global__ void __launch_bounds__(NT) als_dual_tpt_kernel(const DualArgs a) {
 
   const float lam = (float)(a.lambda * (double)n);
   const int tstride = mt * pitch;
+  // One-warp systems with at most 16 Gram tiles (mt <= 5): the sweep would keep half of the lanes idle (the rhs
+  // tile owners and the lanes beyond the tile set), so it is K-split inside the warp instead — lane g * NTRI + r
+  // sums share g of the column chunks of Gram tile r (row-major rank), the owner lanes collect the GS partial
+  // tiles by shuffle in group order (deterministic) and go on as below.
+  constexpr int GS = (TPT == 1 && NT == 32 && 2 * NTRI <= 32) ? 32 / NTRI : 1;
+  if constexpr (GS > 1) {
+    const int g = tid / NTRI, r = tid - g * NTRI;
+    int sI = 0, rem = r;
+    while (rem > sI) { rem -= sI + 1; ++sI; }        // r = sI (sI + 1) / 2 + sL
+    const int sL = rem;
+    float2 acc2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
+    if (g < GS) {
+      const float* ya = Y + sI * pitch;
+      const float* yb = Y + sL * pitch;
+      const int CHT = K4 >> 2;
+      const int c_beg = 4 * ((g * CHT) / GS), c_end = 4 * (((g + 1) * CHT) / GS);
+      for (int c = c_beg; c < c_end; c += 4) {
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          av[i] = *reinterpret_cast<const float4*>(ya + i * tstride + c);
+          bv[i] = *reinterpret_cast<const float4*>(yb + i * tstride + c);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 s2 = acc2[i][j];
+            s2 = __ffma2_rn(make_float2(av[i].x, av[i].y), make_float2(bv[j].x, bv[j].y), s2);
+            s2 = __ffma2_rn(make_float2(av[i].z, av[i].w), make_float2(bv[j].z, bv[j].w), s2);
+            acc2[i][j] = s2;
+          }
+      }
+    }
+    // owner lane of Gram tile (I, L) reads the partial tiles of lanes rank, NTRI + rank, ...
+    const bool own = tI[0] >= 0 && tI[0] < mt;
+    const int rank = own ? tI[0] * (tI[0] + 1) / 2 + tL[0] : 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float part = acc2[i][j].x + acc2[i][j].y;
+        float sum = 0.f;
+#pragma unroll
+        for (int gg = 0; gg < GS; ++gg) sum += __shfl_sync(0xffffffffu, part, rank + gg * NTRI);
+        acc[0][i][j] = own ? sum : 0.f;
+      }
+    if (own && tI[0] == tL[0]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (4 * tI[0] + i < n) acc[0][i][i] += lam;
+        else acc[0][i][i] = 1.0f;
+      }
+    } else if (tI[0] == mt) {
+      const float4 v = *reinterpret_cast<const float4*>(vs + 4 * tL[0]);
+      acc[0][0][0] = v.x; acc[0][0][1] = v.y; acc[0][0][2] = v.z; acc[0][0][3] = v.w;
+    }
+  } else
 #pragma unroll
   for (int q = 0; q < TPT; ++q) {
 #pragma unroll

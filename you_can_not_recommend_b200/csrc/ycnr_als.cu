@@ -220,7 +220,14 @@ void plan_fill(const int32_t* len, int stride, int n_rows, const PlanCfg& cfg, D
 // Row-class thresholds from the options (shared by ycnr_create and the CPU-only planner diagnostics)
 PlanCfg derive_plan_cfg(const ycnr_options& o, bool* use_tc_out) {
   const int k = o.factors_count;
-  const int dflt_dual = std::min(96, std::max(0, ((k - 1) / 4) * 4));
+  const bool tc = o.gram_path == YCNR_GRAM_TC3XTF32 ||
+                  (o.gram_path == YCNR_GRAM_AUTO && (k & 3) == 0 && k <= 256 && k >= 16);
+  // dual / primal crossover.  Measured on B200 at k = 100 (ns per row, whole GPU): dual rows of 22, 23, 24 tile rows
+  // cost 56, 78, 82; a primal row just above the crossover 59 (tensor-core Gram 0.107 per rating + 46 for the k x k
+  // solve) — so rows above 88 ratings go primal there.  Wider systems keep 96 (their solve grows with k^3: 650 ns at
+  // k = 256 against 150 for the largest dual row), FFMA-path systems too (their primal Gram is 4x slower).
+  const int dual_cap = (tc && k <= 112) ? 88 : 96;
+  const int dflt_dual = std::min(dual_cap, std::max(0, ((k - 1) / 4) * 4));
   PlanCfg cfg;
   cfg.dual_max = o.dual_max_cols < 0 ? dflt_dual : std::min(96, o.dual_max_cols);
   cfg.split_cols = o.split_cols > 0 ? std::max(o.split_cols, ycnr::kStageRows) : 4096;
@@ -283,7 +290,8 @@ constexpr int kSlots = 4;
 // noted as DMA segments, others are copied into the slot) and returns; the batch goes to the device as ONE launch
 // group when it holds kBatchFlushRatings ratings, when a large portion arrives, or when the step ends.
 constexpr int64_t kBatchFlushRatings = (int64_t)4 << 20;
-constexpr int64_t kBatchDirectRatings = (int64_t)1 << 20;
+constexpr int64_t kBatchDirectRatings = (int64_t)1 << 20;   // portions in unregistered buffers: staged in the slot up to this size
+constexpr int64_t kBatchMaxRatings = (int64_t)32 << 20;     // portions in page-locked (cached) buffers: DMA'd in place up to this size
 
 struct BatchSeg {
   const int32_t* indx;
@@ -785,7 +793,7 @@ int launch_dual_bin(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t 
 #define YCNR_DUAL_TPT 3
 #endif
 #ifndef YCNR_DUAL2_MIN_MT
-#define YCNR_DUAL2_MIN_MT 5   // measured on B200 (MAL, k = 100): the K-split kernel only wins for mt <= 4
+#define YCNR_DUAL2_MIN_MT 1   // measured on B200 (MAL, k = 100): with its in-warp K-split the one-warp kernel wins everywhere
 #endif
 constexpr int dual2_nt(int mt) { return ((ycnr::dual_ntl(mt) + YCNR_DUAL_TPT - 1) / YCNR_DUAL_TPT + 31) & ~31; }
 constexpr int dual2_tpt(int mt) { return (ycnr::dual_ntl(mt) + dual2_nt(mt) - 1) / dual2_nt(mt); }
@@ -1343,10 +1351,13 @@ int batch_rows_reserve(ycnr_ctx* c, Batch& b, size_t need) {
   return 0;
 }
 
-// Append one small portion (`off` ratings) to the open batch of `kind`; the header is checked on the way
-// (row ids inside [0, lim_rows) and strictly ascending, no negative lengths — see check_header).
-int batch_add(ycnr_ctx* c, int kind, const int32_t* rows, const int32_t* indx, const float* vals, int64_t off,
-              int64_t tag, ycnr_portion_info* info) {
+// Append one small portion to the open batch of `kind` in ONE pass over its header: the rows are written into the
+// batch arrays and checked on the way (row ids inside [0, lim_rows) and strictly ascending, no negative lengths —
+// see check_header; 2 ns per row, the separate check + fill loops cost 4.8).  *taken = false (nothing appended)
+// when the portion turns out to hold kBatchDirectRatings ratings or more: it takes the single-portion path.
+int batch_add(ycnr_ctx* c, int kind, const int32_t* rows, const int32_t* indx, const float* vals, int64_t lim_rows,
+              int64_t tag, ycnr_portion_info* info, bool* taken) {
+  *taken = true;
   Batch& b = c->batch;
   if (b.kind != 0 && b.kind != kind) OK(batch_flush(c));
   if (b.kind == 0) {
@@ -1363,42 +1374,77 @@ int batch_add(ycnr_ctx* c, int kind, const int32_t* rows, const int32_t* indx, c
     OK(batch_rows_reserve(c, b, c->max_batch_rows + c->max_batch_rows / 4 + 4096));
   }
   const int R = rows[0];
-  OK(batch_rows_reserve(c, b, b.n_rows + (size_t)R + (kind == 2 ? (size_t)(off / kRmseChunk) : 0)));
+  // entries of this portion: rows, plus (RMSE) one more per kRmseChunk ratings beyond the first chunk of a row;
+  // the portion holds fewer than kBatchDirectRatings ratings or it is rolled back below
+  OK(batch_rows_reserve(c, b, b.n_rows + (size_t)R + (kind == 2 ? (size_t)(kBatchMaxRatings / kRmseChunk) + 1 : 0)));
   const int64_t base = b.ratings;
   int64_t run = base;
-  if (kind == 2) b.pfirst.push_back((int32_t)b.n_rows);
   const size_t r0 = b.n_rows;
   {
     int32_t* pid = b.ids + r0;
     int32_t* pln = b.len + r0;
     int64_t* pst = b.start + r0;
+    const int32_t* pr = rows + 1;
     size_t e = 0;
+    int64_t prev = -1;
+    int bad = 0;
     if (kind == 1) {
       for (int r = 0; r < R; ++r) {
-        const int32_t n = rows[2 + 2 * (size_t)r];
-        pid[r] = rows[1 + 2 * (size_t)r];
+        const int32_t id = pr[2 * (size_t)r], n = pr[2 * (size_t)r + 1];
+        bad |= (n < 0) | (id < 0) | (id >= lim_rows) | (id <= prev);
+        prev = id;
+        pid[r] = id;
         pln[r] = n;
         pst[r] = run;
         run += n;
       }
       e = (size_t)R;
     } else {   // RMSE: rows cut into entries of at most kRmseChunk ratings (see expand_rmse_entries)
-      for (int r = 0; r < R; ++r) {
-        const int32_t id = rows[1 + 2 * (size_t)r];
-        int32_t n = rows[2 + 2 * (size_t)r];
-        do {
-          const int32_t m = n < kRmseChunk ? n : kRmseChunk;
-          pid[e] = id;
-          pln[e] = m;
-          pst[e] = run;
+      const size_t e_max = (size_t)R + (size_t)(kBatchMaxRatings / kRmseChunk);
+      for (int r = 0; r < R && e < e_max; ++r) {
+        const int32_t id = pr[2 * (size_t)r];
+        int32_t n = pr[2 * (size_t)r + 1];
+        bad |= (n < 0) | (id < 0) | (id >= lim_rows) | (id <= prev);
+        prev = id;
+        pid[e] = id;
+        pst[e] = run;
+        if (n <= kRmseChunk) {
+          pln[e] = n < 0 ? 0 : n;
           ++e;
-          run += m;
-          n -= m;
-        } while (n > 0);
+          run += n < 0 ? 0 : n;
+        } else {
+          pln[e] = kRmseChunk;
+          ++e;
+          run += kRmseChunk;
+          n -= kRmseChunk;
+          while (n > 0 && e < e_max) {
+            const int32_t m = n < kRmseChunk ? n : kRmseChunk;
+            pid[e] = id;
+            pln[e] = m;
+            pst[e] = run;
+            ++e;
+            run += m;
+            n -= m;
+          }
+        }
       }
+    }
+    if (bad) {                                                   // rescan for the message
+      const int rc = check_header(rows, R, lim_rows, &run);
+      return rc ? rc : fail("portion header: invalid");
+    }
+    const int64_t got = run - base;
+    const bool pinned_in = got > 0 && region_pinned(c, indx, (size_t)got * 4) && region_pinned(c, vals, (size_t)got * 4);
+    if (got >= (pinned_in ? kBatchMaxRatings : kBatchDirectRatings) ||
+        (kind == 2 && e >= (size_t)R + (size_t)(kBatchMaxRatings / kRmseChunk))) {
+      // a large portion after all (one that would have to be staged, or a huge one): not for the batch
+      *taken = false;
+      return 0;
     }
     b.n_rows = r0 + e;
   }
+  const int64_t off = run - base;
+  if (kind == 2) b.pfirst.push_back((int32_t)r0);
   const size_t n_added = b.n_rows - r0;
   if (off > 0) {
     const bool direct = region_pinned(c, indx, (size_t)off * 4) && region_pinned(c, vals, (size_t)off * 4);
@@ -1846,12 +1892,11 @@ int ycnr_als_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, cons
     return fail("ycnr_als_portion: call ycnr_start_train_step first");
   const double t0 = now_ms();
   OK(set_device(c));
-  if (rows[0] >= 0 && rows[0] < (1 << 20)) {   // small portions are queued and launched in batches
-    int64_t off = 0;
+  if (rows[0] >= 0 && rows[0] < (1 << 24)) {   // portions are queued and launched in batches
     const int solved_w = c->step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
-    OK(check_header(rows, rows[0], c->fac_rows[solved_w], &off));
-    if (off < kBatchDirectRatings) {
-      OK(batch_add(c, 1, rows, indx, vals, off, 0, info));
+    bool taken = false;
+    OK(batch_add(c, 1, rows, indx, vals, c->fac_rows[solved_w], 0, info, &taken));
+    if (taken) {
       if (info) info->time_ms = now_ms() - t0;
       return 0;
     }
@@ -2026,10 +2071,10 @@ int ycnr_rmse_portion_async(ycnr_ctx* c, const int32_t* rows, const int32_t* ind
       }
     }
   }
-  if (rows[0] >= 0 && rows[0] < (1 << 20)) {
-    int64_t off = 0;
-    OK(check_header(rows, rows[0], c->fac_rows[YCNR_USER_FACTORS], &off));
-    if (off < kBatchDirectRatings) return batch_add(c, 2, rows, indx, vals, off, tag, nullptr);
+  if (rows[0] >= 0 && rows[0] < (1 << 20)) {   // (portions of a million rows keep the device-side header unpack)
+    bool taken = false;
+    OK(batch_add(c, 2, rows, indx, vals, c->fac_rows[YCNR_USER_FACTORS], tag, nullptr, &taken));
+    if (taken) return 0;
   }
   ycnr_portion_info pi;
   double rat = 0.0;
