@@ -161,9 +161,11 @@ int ycnr_start_calc_rmse(ycnr_ctx* ctx, int32_t step_type, double global_avg_shi
 int ycnr_rmse_portion(ycnr_ctx* ctx, const int32_t* rmse_rows, const int32_t* rmse_indx,
                       const float* rmse_vals, ycnr_portion_info* info_out);
 
-/* Portions of fewer than 2^20 ratings (the reference default is 10 000, EmfBase.js:97-103) are QUEUED by
- * ycnr_als_portion and launched in batches of ~4 M ratings (or at ycnr_end_train_step): the call returns the
- * 'completedPortion' fields at once, the rows are in the host segment after ycnr_end_train_step as before.
+/* Portions (the reference default is 10 000 ratings, EmfBase.js:97-103) are QUEUED by ycnr_als_portion and launched
+ * in batches of ~4 M ratings (or at ycnr_end_train_step): the call checks the header, returns the 'completedPortion'
+ * fields at once, the rows are in the host segment after ycnr_end_train_step as before.  Exceptions: a portion of
+ * 2^20 ratings or more in UNREGISTERED buffers (it would have to be staged) and portions of 2^24 rows take the
+ * single-portion path at once.
  * The RMSE twin: ycnr_rmse_portion_async queues a portion under a caller tag (portionNo); ycnr_rmse_poll hands
  * back the completed portions in the order they were queued — wait != 0 flushes the queue and waits for all of
  * them (the worker's 'completedPortion' replies are asynchronous messages upstream as well, EmfWorker.js:304-314).

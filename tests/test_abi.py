@@ -59,7 +59,8 @@ def test_option_validation_messages():
 def test_sass_carries_the_blackwell_instructions_the_design_claims():
     """cuobjdump -sass of the built library (no GPU needed): the Gram kernel really issues tcgen05 MMAs into TMEM
     (UTCHMMA — kind::tf32 shows under this mnemonic —, UTCBAR = tcgen05.commit, LDTM = tcgen05.ld, UTCATOMSWS = TMEM
-    alloc), gathers with cp.async (LDGSTS) and L2 prefetches (CCTL.E.PF2); the dual kernels use packed FP32 FMAs
+    alloc), gathers with TMA tile::gather4 (UTMALDG; cp.async = LDGSTS for the column-block passes) and L2 prefetches
+    (CCTL.E.PF2); the dual kernels use packed FP32 FMAs
     (FFMA2) and the factorisation the MUFU reciprocal square root; the by-item counting sort ranks with MATCH."""
     import subprocess
     sass = subprocess.run(["cuobjdump", "-sass", build.build_cuda()], capture_output=True, text=True).stdout
@@ -73,9 +74,10 @@ def test_sass_carries_the_blackwell_instructions_the_design_claims():
             per_fn[fn].append(line)
     def has(fn_part, mnemonic):
         return any(fn_part in f and any(mnemonic in ln for ln in body) for f, body in per_fn.items())
-    for m in ("UTCHMMA", "UTCBAR", "LDTM", "UTCATOMSWS", "LDGSTS", "CCTL.E.PF2", "SYNCS"):
-        assert has("gram_tc_kernel", m), m
-    assert has("als_dual_kernel", "FFMA2") and has("als_dual_kernel", "MUFU.RSQ") and has("als_dual_kernel", "LDGSTS")
+    for m in ("UTCHMMA", "UTCBAR", "LDTM", "UTCATOMSWS", "LDGSTS", "CCTL.E.PF2", "SYNCS", "UTMALDG"):
+        assert has("gram_tc_kernel", m), m                  # UTMALDG: the TMA tile::gather4 loads of the operand atoms
+    assert has("als_dual_tpt_kernel", "UBLKCP")             # TMA bulk copies of the gathered rows
+    assert has("als_dual_tpt_kernel", "FFMA2") and has("als_dual_tpt_kernel", "MUFU.RSQ") and has("als_dual_tpt_kernel", "LDGSTS")
     assert has("als_primal_kernel", "MUFU.RSQ")
     assert has("item_scatter_kernel", "MATCH")
     assert not has("gram_tc_kernel", "HMMA.") or True      # no legacy mma.sync path is required anywhere

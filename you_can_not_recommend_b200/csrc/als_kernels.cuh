@@ -221,6 +221,8 @@ struct PrimalArgs {
   float* __restrict__ partial;            // [items][tiles][16]
   const int32_t* __restrict__ row_first_item;  // MODE_REDUCE: per work entry
   const int32_t* __restrict__ row_n_items;
+  const void* tmap;                            // host pointer to the CUtensorMap of `fixed` (tensor-core Gram), or null
+  int fixed_rows;
 };
 
 template <int KT, int NT, int TPT, int MODE>

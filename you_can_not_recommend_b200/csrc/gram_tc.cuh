@@ -56,6 +56,8 @@
 // exposed) -> MMA; loaders spent 77 % and the epilogue 97 % of their samples waiting, i.e. the ring was bound
 // by the two producer legs, which v4 halves.  v4: tensor pipe 42-50 % active, LSU data pipe 64 %.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only: the encode function is fetched through cudaGetDriverEntryPoint)
+
 #include "als_kernels.cuh"
 #include "common.cuh"
 
@@ -109,6 +111,13 @@ struct GramTcArgs {
   // One pass over all columns (k <= 124): col_a = 0, chunks_a = KT.  Systems with k > 124 are covered by one
   // pass per PAIR of column blocks (blocks of w <= 60 columns, 2 w + 4 <= 128), see launch_primal_blocks.
   int col_a, col_b, chunks_a;
+  // TMA gather (one-pass systems): tensor map over the fixed matrix [fixed_rows x k] fp32, box {32 columns, 1 row},
+  // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  One cp.async.bulk.tensor.2d...tile::gather4 lands four gathered rows x 32
+  // columns as exactly one operand atom (verified with scripts/micro/tma_gather4_probe.cu: row r of the tile at
+  // byte r * 128, its 32-byte chunks XOR-swizzled by r, columns >= k zero-filled) — without LSU wavefronts.
+  CUtensorMap tmap;
+  int use_tma;
+  int fixed_rows;
   uint32_t variant;              // diagnostics: 16 = splitters also overwrite the H columns with explicitly masked values
 };
 
@@ -200,7 +209,7 @@ struct TcItemIter {
 };
 
 template <int KT>
-__global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const GramTcArgs a) {
+__global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __grid_constant__ GramTcArgs a) {
   using Cfg = TcCfg<KT>;
   constexpr int NCH = Cfg::NCH, NC = Cfg::NC, XP = Cfg::XP;
   constexpr int STAGES = Cfg::STAGES;
@@ -231,7 +240,9 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, 2);     // two splitter warps
       mbar_init(empty0 + 8 * s, 1);
-      mbar_init(raw0 + 8 * s, 64);     // every lane of the two loader warps, when its copies have landed
+      // cp.async path: every lane of the two loader warps arrives when its copies have landed;
+      // TMA path: one arrive.expect_tx per loader warp, the copy engine completes the bytes
+      mbar_init(raw0 + 8 * s, a.use_tma ? 2 : 64);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf0 + 8 * b, 1);
@@ -306,6 +317,31 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
         // this lane's arrival on the stage's raw barrier fires when its copies have landed
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(raw0 + 8 * s_own) : "memory");
       };
+      // TMA variant of issue(): lane l < 16 lands the atom (group g = l / 4 of four ratings, panel p = l % 4).
+      const bool tma = a.use_tma != 0;
+      const int hp = (k + 31) >> 5;                     // panels that hold real columns
+      const uint64_t tmap_addr = reinterpret_cast<uint64_t>(&a.tmap);
+      auto issue_tma = [&](uint32_t use, int col, uint32_t vm) {
+        mbar_wait(empty0 + 8 * s_own, (use & 1u) ^ 1u);
+        const int g = (lane >> 2) & 3, p = lane & 3;
+        int ir[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = __shfl_sync(0xffffffffu, col, 4 * g + q);
+          ir[q] = ((vm >> (4 * g + q)) & 1u) ? c : a.fixed_rows;      // out-of-range row: zero-filled by the copy engine
+        }
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(raw0 + 8 * s_own),
+                       "r"((uint32_t)(4 * hp * 512))
+                       : "memory");
+        __syncwarp();
+        if (lane < 16 && p < hp)
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(
+                  smem_u32(sb + p * kTcPanelBytes + g * 512)),
+              "l"(tmap_addr), "r"(raw0 + 8 * s_own), "r"(32 * p), "r"(ir[0]), "r"(ir[1]), "r"(ir[2]), "r"(ir[3])
+              : "memory");
+      };
       // L2 prefetch of the rows this warp will gather kTcPrefetchUses ring cycles from now: the bytes in
       // flight against HBM latency are no longer capped by the ring's shared memory (6 x 32 ratings x 400 B).
       // Lane l asks for 128-byte line (l >> 4) and (l >> 4) + 2 of rating l & 15: a 400-byte row that starts
@@ -353,7 +389,8 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
           px.advance(a, STAGES);
           load_pf_ids(px, pcol);
         }
-        issue(use++, colA, vmA, eA);
+        if (tma) issue_tma(use++, colA, vmA);
+        else issue(use++, colA, vmA, eA);
         if (!ix.valid(a)) break;
         ix.advance(a, STAGES);
         load_ids(ix, colA, vmA, eA);
@@ -362,20 +399,36 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
           px.advance(a, STAGES);
           load_pf_ids(px, pcol);
         }
-        issue(use++, colB, vmB, eB);
+        if (tma) issue_tma(use++, colB, vmB);
+        else issue(use++, colB, vmB, eB);
       }
       cp_async_wait<0>();
     } else {
       // ============================ splitters ============================
       const bool mask_head = (a.variant & 16u) != 0;
+      const bool tma = a.use_tma != 0;
       for (uint32_t use = 0; ix.valid(a); ++use, ix.advance(a, STAGES)) {
+        // TMA path: the copy engine zero-fills column KP, so the ratings are fetched here (lane r: rating r of this
+        // half, requested before the wait) and written as the (val, 0, 0, 0) chunk by the lane that owns it
+        float myval = 0.f;
+        if (tma && lane < HR) {
+          const int idx = ix.st * kTcStageRows + half * HR + lane;
+          if (idx < ix.seg_len) myval = __ldg(a.rows.vals + ix.seg_beg + idx);
+        }
         mbar_wait(raw0 + 8 * s_own, use & 1u);
-        if (lane < NCH) {
 #pragma unroll
-          for (int r0 = 0; r0 < HR; r0 += 4) {
+        for (int r0 = 0; r0 < HR; r0 += 4) {
+          float vj[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) vj[j] = __shfl_sync(0xffffffffu, myval, r0 + j);
+          if (lane < NCH) {
             float4 v[4];
+            const bool val_lane = tma && lane == NCH - 1;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(sb + oh4[j] + (r0 >> 2) * 512);
+            for (int j = 0; j < 4; ++j) {
+              if (val_lane) v[j] = make_float4(vj[j], 0.f, 0.f, 0.f);
+              else v[j] = *reinterpret_cast<const float4*>(sb + oh4[j] + (r0 >> 2) * 512);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float4 h, l;
@@ -388,6 +441,7 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const Gr
               l.z = v[j].z - h.z;
               l.w = v[j].w - h.w;
               if (mask_head) *reinterpret_cast<float4*>(sb + oh4[j] + (r0 >> 2) * 512) = h;
+              else if (val_lane) *reinterpret_cast<float4*>(sb + oh4[j] + (r0 >> 2) * 512) = v[j];
               *reinterpret_cast<float4*>(sb + ol4[j] + (r0 >> 2) * 512) = l;
             }
           }

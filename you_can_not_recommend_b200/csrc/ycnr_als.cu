@@ -342,6 +342,9 @@ struct ycnr_ctx {
   int fused_max = 0;       // rows longer than this go through the partial (+reduce) kernels
   bool use_tc = false;     // tcgen05 3xTF32 Gram for the partial kernels
   bool tc_tested = false;  // tc_self_test ran on this context's device
+  CUtensorMap tmap[2];     // TMA descriptors of the two replicas (box 32 columns x 1 row, SWIZZLE_128B_ATOM_32B)
+  bool tma_ok[2] = {false, false};
+  bool no_tma = false;     // YCNR_NO_TMA=1: keep the cp.async gather (A/B measurements)
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D of portion inputs, overlaps the previous portion's kernels
@@ -539,6 +542,7 @@ int tc_self_test(ycnr_ctx* c) {
   t.n_items = 1;
   t.split_cols = 4096;
   t.chunks_a = 1 << 20;
+  t.use_tma = 0;
   const size_t smem = gram_tc_smem_bytes<KT>();
   OK(ensure_dynamic_smem(c, reinterpret_cast<const void*>(&gram_tc_kernel<KT>), smem));
   for (int v = 0; v < 2; ++v) {
@@ -589,6 +593,12 @@ int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int item_from, int n
     t.col_a = cm.col_a;
     t.col_b = cm.col_b;
     t.chunks_a = cm.chunks_a;
+    t.use_tma = 0;
+    t.fixed_rows = pa.fixed_rows;
+    if (pa.tmap && cm.chunks_a >= KT && !c->no_tma) {   // one-pass systems gather with the copy engine
+      memcpy(&t.tmap, pa.tmap, sizeof(CUtensorMap));
+      t.use_tma = 1;
+    }
     t.variant = (uint32_t)c->opts.tc_variant;
     t.prefetch = pa.fixed_bytes > ((size_t)48 << 20) ? 1 : 0;
     const size_t smem = gram_tc_smem_bytes<KT>();
@@ -855,6 +865,8 @@ int run_als(ycnr_ctx* c, int step_type, const RowsView& view, const DevPlan& p, 
   a.rows = view;
   a.fixed = c->d_fac[fixed];
   a.fixed_bytes = (size_t)c->fac_rows[fixed] * c->k * sizeof(float);
+  a.tmap = c->tma_ok[fixed] ? &c->tmap[fixed] : nullptr;
+  a.fixed_rows = (int)c->fac_rows[fixed];
   a.k = c->k;
   a.lambda = lambda;
   a.dst = d.dst;
@@ -1720,6 +1732,28 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   }
   for (auto& e : c->chunk_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (int w = 0; w < 2; ++w) CU(cudaMalloc(&c->d_fac[w], (size_t)c->fac_rows[w] * c->k * sizeof(float)));
+  c->no_tma = getenv("YCNR_NO_TMA") != nullptr;
+  if (use_tc && (c->k & 3) == 0) {
+    // TMA descriptors for the gather of the tensor-core Gram (row stride k * 4 bytes is a multiple of 16)
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeFn enc = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&enc, cudaEnableDefault, &qres) != cudaSuccess) {
+      cudaGetLastError();
+      enc = nullptr;
+    }
+    for (int w = 0; w < 2 && enc; ++w) {
+      cuuint64_t gdim[2] = {(cuuint64_t)c->k, (cuuint64_t)c->fac_rows[w]};
+      cuuint64_t gstr[1] = {(cuuint64_t)c->k * sizeof(float)};
+      cuuint32_t box[2] = {32, 1};
+      cuuint32_t estr[2] = {1, 1};
+      c->tma_ok[w] = enc(&c->tmap[w], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->d_fac[w], gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+  }
   CU(cudaMalloc(&c->d_bad, sizeof(int32_t)));
   CU(cudaMemset(c->d_bad, 0, sizeof(int32_t)));
   CU(cudaMallocHost(&c->h_bad, sizeof(int32_t)));
