@@ -1733,6 +1733,7 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   for (auto& e : c->chunk_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (int w = 0; w < 2; ++w) CU(cudaMalloc(&c->d_fac[w], (size_t)c->fac_rows[w] * c->k * sizeof(float)));
   c->no_tma = getenv("YCNR_NO_TMA") != nullptr;
+  if (const char* e = getenv("YCNR_TC_VARIANT")) c->opts.tc_variant = atoi(e);   // diagnostics (gram_tc.cuh: variant bits)
   if (use_tc && (c->k & 3) == 0) {
     // TMA descriptors for the gather of the tensor-core Gram (row stride k * 4 bytes is a multiple of 16)
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
