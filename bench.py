@@ -468,7 +468,7 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args.e2e_portion, True, max(1, args.steps), max(1, min(args.warmup, 2)))
+        e2e = run_e2e(args.e2e_portion, True, max(1, args.steps), max(1, args.warmup))
         if args.e2e_large_portion and world == 1:      # (a few 8 M-rating portions cannot be balanced over ranks)
             e2e["large_portions"] = run_e2e(args.e2e_large_portion, False, max(1, min(args.steps, 3)), 1)
         if args.e2e_python_steps:

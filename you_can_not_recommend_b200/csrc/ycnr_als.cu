@@ -5,7 +5,12 @@
 #include "ycnr_als.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -326,6 +331,84 @@ struct RmseInflight {
   bool live = false;
 };
 
+// ---- host worker pool for the multi-portion entry points -------------------------------------------------
+// ycnr_als_portions / ycnr_rmse_portions_async see all portions of a half-step (an RMSE pass) at once: their
+// headers (1.75 M rows per pass on MAL: 4.6 ms single-threaded, more than the pass's kernels and DMA together)
+// are scanned and written into the batch arrays by a few threads.  The caller takes part; workers sleep on a
+// condition variable between regions.
+struct WorkPool {
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  const std::function<void(int)>* fn = nullptr;
+  int n_tasks = 0, active = 0;
+  std::atomic<int> next{0};
+  uint64_t gen = 0;
+  bool stop = false;
+  void start(int workers) {
+    for (int i = 0; i < workers; ++i)
+      th.emplace_back([this] {
+        uint64_t seen = 0;
+        for (;;) {
+          const std::function<void(int)>* f;
+          int n;
+          {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_go.wait(lk, [&] { return stop || gen != seen; });
+            if (stop) return;
+            seen = gen;
+            f = fn;
+            n = n_tasks;
+          }
+          for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) (*f)(i);
+          std::lock_guard<std::mutex> lk(mu);
+          if (--active == 0) cv_done.notify_one();
+        }
+      });
+  }
+  void run(int n, const std::function<void(int)>& f) {
+    if (th.empty() || n < 2) {
+      for (int i = 0; i < n; ++i) f(i);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      fn = &f;
+      n_tasks = n;
+      next.store(0);
+      active = (int)th.size();
+      ++gen;
+    }
+    cv_go.notify_all();
+    for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i);
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return active == 0; });
+  }
+  void shutdown() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv_go.notify_all();
+    for (auto& t : th) t.join();
+    th.clear();
+  }
+};
+
+// What a scan of a portion header yields without writing anything (multi-portion entry points)
+struct PortionPre {
+  int64_t entries = 0;    // rows (ALS) / work entries of at most kRmseChunk ratings (RMSE)
+  int64_t ratings = 0;
+  int bad = 0;
+};
+// A header whose rows still have to be written into the open batch's arrays
+struct FillTask {
+  int kind;
+  const int32_t* rows;
+  size_t r0;              // first entry in the batch arrays
+  int64_t base;           // first rating in the batch's device arrays
+};
+
 struct ProfRec {
   int cls;
   cudaEvent_t a, b;
@@ -392,6 +475,7 @@ struct ycnr_ctx {
   size_t max_host3 = 0;   // largest plan block any slot has needed: every slot is grown to it at its next use
   size_t max_slot_dev = 0;
   size_t max_batch_rows = 0;
+  int flushes_in_pass = 0;   // batches flushed since the step / RMSE pass began: the first ones are smaller (see batch_add)
   int64_t batch_flush_ratings = kBatchFlushRatings;   // YCNR_BATCH_FLUSH overrides (tests exercise many flushes)
   std::vector<RmseInflight> rmse_inflight;
   std::vector<int> rmse_order;                                    // live entries of rmse_inflight, oldest first
@@ -427,7 +511,9 @@ struct ycnr_ctx {
   // k x k solves (k <= 128) by the row-register LDL^T kernel (als_solve_rows_kernel) instead of the tile Cholesky;
   // YCNR_SOLVE_ROWS=0/1 overrides
   bool solve_rows = false;       // experiment, off: 30 ms against 9 ms for the tile Cholesky
-  double t_parse = 0, t_slot_wait = 0, t_copy_issue = 0, t_launch = 0;
+  WorkPool pool;
+  std::vector<FillTask> fill_tasks;   // deferred header writes of the open batch (multi-portion entry points)
+  double t_parse = 0, t_slot_wait = 0, t_copy_issue = 0, t_launch = 0, t_add = 0, t_rmse_calls = 0, t_fill = 0, t_scan = 0;
   int t_portions = 0;
   // kernels whose dynamic shared-memory limit was raised on this context's device (function attributes are
   // per device: a process-wide flag would skip the second device of a process)
@@ -1380,6 +1466,7 @@ int acquire_slot(ycnr_ctx* c, Slot** out) {
 }
 
 int batch_flush(ycnr_ctx* c);
+int run_fill_tasks(ycnr_ctx* c);
 
 // Row arrays of the open batch live in the slot's page-locked host2 buffer (start i64[cap] | ids i32[cap] |
 // len i32[cap]) and are DMA'd from there: the per-row loop below is the only pass over the header.
@@ -1406,14 +1493,96 @@ int batch_rows_reserve(ycnr_ctx* c, Batch& b, size_t need) {
   return 0;
 }
 
+// Scan of a portion header without writing anything: entries, ratings and the validity flags batch_add checks.
+PortionPre scan_header(int kind, const int32_t* rows, int64_t lim_rows) {
+  PortionPre p;
+  const int R = rows[0];
+  if (R < 0 || R >= (1 << 24)) return p;       // not a batch candidate: the single-portion path reports it
+  const int32_t* pr = rows + 1;
+  int64_t prev = -1, ratings = 0, entries = 0;
+  int bad = 0;
+  for (int r = 0; r < R; ++r) {
+    const int32_t id = pr[2 * (size_t)r], n = pr[2 * (size_t)r + 1];
+    bad |= (n < 0) | (id < 0) | (id >= lim_rows) | (id <= prev);
+    prev = id;
+    if (kind == 1) {
+      ratings += n;
+    } else {
+      ratings += n < 0 ? 0 : n;
+      entries += n <= kRmseChunk ? 1 : (n + kRmseChunk - 1) / kRmseChunk;
+    }
+  }
+  p.entries = kind == 1 ? R : entries;
+  p.ratings = ratings;
+  p.bad = bad;
+  return p;
+}
+
+// Write the rows (RMSE: work entries) of a scanned, valid header into the batch arrays; run = first rating
+void fill_header(int kind, const int32_t* rows, int32_t* pid, int32_t* pln, int64_t* pst, int64_t run) {
+  const int R = rows[0];
+  const int32_t* pr = rows + 1;
+  if (kind == 1) {
+    for (int r = 0; r < R; ++r) {
+      const int32_t n = pr[2 * (size_t)r + 1];
+      pid[r] = pr[2 * (size_t)r];
+      pln[r] = n;
+      pst[r] = run;
+      run += n;
+    }
+    return;
+  }
+  size_t e = 0;
+  for (int r = 0; r < R; ++r) {
+    const int32_t id = pr[2 * (size_t)r];
+    int32_t n = pr[2 * (size_t)r + 1];
+    do {
+      const int32_t m = n < kRmseChunk ? n : kRmseChunk;
+      pid[e] = id;
+      pln[e] = m;
+      pst[e] = run;
+      ++e;
+      run += m;
+      n -= m;
+    } while (n > 0);
+  }
+}
+
+// Deferred header writes of the open batch (queued by the multi-portion entry points), spread over the pool
+int run_fill_tasks(ycnr_ctx* c) {
+  if (c->fill_tasks.empty()) return 0;
+  const double t0 = c->trace ? now_ms() : 0.0;
+  Batch& b = c->batch;
+  const std::vector<FillTask>& tasks = c->fill_tasks;
+  const int n = (int)tasks.size();
+  constexpr int kPer = 8;
+  const std::function<void(int)> fn = [&](int blk) {
+    const int i1 = std::min(n, (blk + 1) * kPer);
+    for (int i = blk * kPer; i < i1; ++i) {
+      const FillTask& t = tasks[i];
+      fill_header(t.kind, t.rows, b.ids + t.r0, b.len + t.r0, b.start + t.r0, t.base);
+    }
+  };
+  c->pool.run((n + kPer - 1) / kPer, fn);
+  c->fill_tasks.clear();
+  if (c->trace) c->t_fill += now_ms() - t0;
+  return 0;
+}
+
 // Append one small portion to the open batch of `kind` in ONE pass over its header: the rows are written into the
 // batch arrays and checked on the way (row ids inside [0, lim_rows) and strictly ascending, no negative lengths —
 // see check_header; 2 ns per row, the separate check + fill loops cost 4.8).  *taken = false (nothing appended)
 // when the portion turns out to hold kBatchDirectRatings ratings or more: it takes the single-portion path.
+// pre != nullptr (multi-portion entry points): the header was scanned already (scan_header); its rows are written
+// later by run_fill_tasks, before the batch is flushed and before the entry point returns.
 int batch_add(ycnr_ctx* c, int kind, const int32_t* rows, const int32_t* indx, const float* vals, int64_t lim_rows,
-              int64_t tag, ycnr_portion_info* info, bool* taken) {
+              int64_t tag, ycnr_portion_info* info, bool* taken, const PortionPre* pre = nullptr) {
   *taken = true;
   Batch& b = c->batch;
+  struct AddTimer {
+    ycnr_ctx* c; double t0;
+    ~AddTimer() { c->t_add += now_ms() - t0; }
+  } add_timer{c, c->trace ? now_ms() : 0.0};
   if (b.kind != 0 && b.kind != kind) OK(batch_flush(c));
   if (b.kind == 0) {
     OK(acquire_slot(c, &b.slot));
@@ -1443,7 +1612,11 @@ int batch_add(ycnr_ctx* c, int kind, const int32_t* rows, const int32_t* indx, c
     size_t e = 0;
     int64_t prev = -1;
     int bad = 0;
-    if (kind == 1) {
+    if (pre) {
+      bad = pre->bad;
+      e = (size_t)pre->entries;
+      run = base + pre->ratings;
+    } else if (kind == 1) {
       for (int r = 0; r < R; ++r) {
         const int32_t id = pr[2 * (size_t)r], n = pr[2 * (size_t)r + 1];
         bad |= (n < 0) | (id < 0) | (id >= lim_rows) | (id <= prev);
@@ -1497,6 +1670,7 @@ int batch_add(ycnr_ctx* c, int kind, const int32_t* rows, const int32_t* indx, c
       return 0;
     }
     b.n_rows = r0 + e;
+    if (pre) c->fill_tasks.push_back({kind, rows, r0, base});
   }
   const int64_t off = run - base;
   if (kind == 2) b.pfirst.push_back((int32_t)r0);
@@ -1513,7 +1687,8 @@ int batch_add(ycnr_ctx* c, int kind, const int32_t* rows, const int32_t* indx, c
         region_pinned(c, last->vals, (size_t)(last->n + gap + off) * 4)) {
       last->n += gap + off;
       if (gap) {
-        for (size_t r = 0; r < n_added; ++r) b.start[r0 + r] += gap;
+        if (pre) c->fill_tasks.back().base += gap;
+        else for (size_t r = 0; r < n_added; ++r) b.start[r0 + r] += gap;
         run += gap;
       }
     } else if (!direct && last && !last->direct) {
@@ -1548,13 +1723,19 @@ int batch_add(ycnr_ctx* c, int kind, const int32_t* rows, const int32_t* indx, c
     b.infos.push_back(pi);
   }
   c->t_portions++;
-  if (b.ratings >= c->batch_flush_ratings) OK(batch_flush(c));
+  // ramp-up: the first batches of a step are an eighth, a quarter, half of the flush size — the GPU starts after
+  // ~0.5 M ratings have been queued instead of 4 M (measured on MAL byUser: the step began with ~3 ms of host work
+  // and DMA before the first kernel)
+  const int64_t flush_at = std::max<int64_t>(1, c->batch_flush_ratings >> std::max(0, 3 - c->flushes_in_pass));
+  if (b.ratings >= flush_at) OK(batch_flush(c));
   return 0;
 }
 
 int batch_flush(ycnr_ctx* c) {
   Batch& b = c->batch;
   if (b.kind == 0) return 0;
+  OK(run_fill_tasks(c));
+  c->flushes_in_pass++;
   const int kind = b.kind;
   b.kind = 0;
   Slot& sl = *b.slot;
@@ -1760,6 +1941,12 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   c->trace = getenv("YCNR_TRACE") != nullptr;
   if (const char* e = getenv("YCNR_BATCH_FLUSH")) c->batch_flush_ratings = std::max<int64_t>(1, atoll(e));
   if (const char* e = getenv("YCNR_SPREAD_BULK")) c->spread_bulk = atoi(e) ? 1 : 0;
+  {   // host threads of the multi-portion entry points (the caller is one of them)
+    const int hw = (int)std::thread::hardware_concurrency();
+    int threads = std::max(1, std::min(6, hw / 4));
+    if (const char* e = getenv("YCNR_HOST_THREADS")) threads = std::max(1, std::min(64, atoi(e)));
+    c->pool.start(threads - 1);
+  }
   if (const char* e = getenv("YCNR_DUAL_WARP")) c->dual_warp_mask = (uint32_t)strtoul(e, nullptr, 16);
   if (const char* e = getenv("YCNR_SOLVE_ROWS")) c->solve_rows = atoi(e) != 0;
   c->fac_rows[0] = o->total_users;
@@ -1811,6 +1998,7 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
 
 int ycnr_destroy(ycnr_ctx* c) {
   if (!c) return 0;
+  c->pool.shutdown();
   cudaSetDevice(c->opts.device);
   cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->stream);
@@ -1957,6 +2145,7 @@ int ycnr_start_train_step(ycnr_ctx* c, int32_t step_type) {
   OK(set_device(c));
   OK(rmse_collect(c, true));   // (nothing is left queued from an earlier pass)
   c->step_type = step_type;
+  c->flushes_in_pass = 0;
   c->solved_ranges.clear();
   const int solved = step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
   c->fac_version[solved]++;   // peers may store into this replica during the step even if no portion arrives here
@@ -1965,8 +2154,16 @@ int ycnr_start_train_step(ycnr_ctx* c, int32_t step_type) {
   return 0;
 }
 
+static int als_portion_impl(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals,
+                            ycnr_portion_info* info, const PortionPre* pre);
+
 int ycnr_als_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals,
                      ycnr_portion_info* info) {
+  return als_portion_impl(c, rows, indx, vals, info, nullptr);
+}
+
+static int als_portion_impl(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals,
+                            ycnr_portion_info* info, const PortionPre* pre) {
   if (!c || !rows || !indx || !vals) return fail("ycnr_als_portion: null argument");
   if (c->step_type != YCNR_BY_USER && c->step_type != YCNR_BY_ITEM)
     return fail("ycnr_als_portion: call ycnr_start_train_step first");
@@ -1975,7 +2172,7 @@ int ycnr_als_portion(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, cons
   if (rows[0] >= 0 && rows[0] < (1 << 24)) {   // portions are queued and launched in batches
     const int solved_w = c->step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
     bool taken = false;
-    OK(batch_add(c, 1, rows, indx, vals, c->fac_rows[solved_w], 0, info, &taken));
+    OK(batch_add(c, 1, rows, indx, vals, c->fac_rows[solved_w], 0, info, &taken, pre));
     if (taken) {
       if (info) info->time_ms = now_ms() - t0;
       return 0;
@@ -2041,10 +2238,11 @@ int ycnr_end_train_step(ycnr_ctx* c) {
   const double ts1 = now_ms();
   if (c->trace) {
     fprintf(stderr, "[ycnr trace] step %d: %d portions, host parse %.2f ms, slot wait %.2f ms, copy issue %.2f ms, "
-            "launch %.2f ms, final sync %.2f ms\n", c->step_type, c->t_portions, c->t_parse, c->t_slot_wait,
-            c->t_copy_issue, c->t_launch, ts1 - ts0);
+            "launch %.2f ms, batch_add total %.2f ms, header scan %.2f ms, header fill %.2f ms, final sync %.2f ms\n",
+            c->step_type, c->t_portions, c->t_parse, c->t_slot_wait, c->t_copy_issue, c->t_launch, c->t_add, c->t_scan,
+            c->t_fill, ts1 - ts0);
   }
-  c->t_parse = c->t_slot_wait = c->t_copy_issue = c->t_launch = 0;
+  c->t_parse = c->t_slot_wait = c->t_copy_issue = c->t_launch = c->t_add = c->t_fill = c->t_scan = 0;
   c->t_portions = 0;
   if (c->d2h_pending) {
     CU(cudaStreamSynchronize(c->d2h_stream));
@@ -2067,6 +2265,7 @@ int ycnr_start_calc_rmse(ycnr_ctx* c, int32_t step_type, double shift) {
   OK(set_device(c));
   OK(rmse_collect(c, true));   // a queued batch still belongs to the previous pass (its shift)
   c->step_type = step_type;
+  c->flushes_in_pass = 0;
   c->rmse_shift = shift;
   OK(ensure_fixed_current(c, YCNR_USER_FACTORS));
   OK(ensure_fixed_current(c, YCNR_ITEM_FACTORS));
@@ -2123,7 +2322,15 @@ static int rmse_portion_sync(ycnr_ctx* c, const int32_t* rows, const int32_t* in
   return 0;
 }
 
+static int rmse_portion_async_impl(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals, int64_t tag,
+                                   const PortionPre* pre);
+
 int ycnr_rmse_portion_async(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals, int64_t tag) {
+  return rmse_portion_async_impl(c, rows, indx, vals, tag, nullptr);
+}
+
+static int rmse_portion_async_impl(ycnr_ctx* c, const int32_t* rows, const int32_t* indx, const float* vals, int64_t tag,
+                                   const PortionPre* pre) {
   if (!c || !rows || !indx || !vals) return fail("ycnr_rmse_portion_async: null argument");
   if (c->step_type != YCNR_RMSE_VALIDATE && c->step_type != YCNR_RMSE_TEST)
     return fail("ycnr_rmse_portion_async: call ycnr_start_calc_rmse first");
@@ -2153,7 +2360,7 @@ int ycnr_rmse_portion_async(ycnr_ctx* c, const int32_t* rows, const int32_t* ind
   }
   if (rows[0] >= 0 && rows[0] < (1 << 20)) {   // (portions of a million rows keep the device-side header unpack)
     bool taken = false;
-    OK(batch_add(c, 2, rows, indx, vals, c->fac_rows[YCNR_USER_FACTORS], tag, nullptr, &taken));
+    OK(batch_add(c, 2, rows, indx, vals, c->fac_rows[YCNR_USER_FACTORS], tag, nullptr, &taken, pre));
     if (taken) return 0;
   }
   ycnr_portion_info pi;
@@ -2169,7 +2376,15 @@ int ycnr_rmse_poll(ycnr_ctx* c, int32_t wait, int32_t max_out, int64_t* tags_out
   if (!c || !n_out || max_out < 0 || (max_out && (!tags_out || !infos_out))) return fail("ycnr_rmse_poll: bad argument");
   OK(set_device(c));
   *n_out = 0;
+  const double tc0 = now_ms();
   OK(rmse_collect(c, wait != 0));
+  if (c->trace && wait) {
+    fprintf(stderr, "[ycnr trace] rmse pass %d: %d portions, calls %.2f ms (batch_add %.2f incl. flushes: plan/pack %.2f, "
+            "slot wait %.2f, copy issue %.2f), final collect %.2f ms\n", c->step_type, c->t_portions, c->t_rmse_calls,
+            c->t_add, c->t_parse, c->t_slot_wait, c->t_copy_issue, now_ms() - tc0);
+    c->t_parse = c->t_slot_wait = c->t_copy_issue = c->t_launch = c->t_add = c->t_rmse_calls = 0;
+    c->t_portions = 0;
+  }
   if (*c->h_bad) {
     *c->h_bad = 0;
     CU(cudaMemset(c->d_bad, 0, sizeof(int32_t)));
@@ -2192,18 +2407,59 @@ int ycnr_rmse_poll(ycnr_ctx* c, int32_t wait, int32_t max_out, int64_t* tags_out
 
 // n calls of ycnr_als_portion / ycnr_rmse_portion_async issued from native code (a binding whose per-call overhead
 // matters — a Python loop spends ~10 us per message — hands over the pointers of n filled portion buffers).
+// The headers are scanned by the context's worker pool first (scan_header), the calls then run in order on the
+// calling thread with the scan results, and the rows of the queued portions are written by the pool again
+// (run_fill_tasks) — before a batch goes to the device and before this function returns, so the caller may reuse
+// the header buffers afterwards exactly as after n single calls.
+// (in groups of kScanGroup portions, so that the first batch is on its way after a fraction of a millisecond)
+constexpr int kScanGroup = 512;
+static void scan_headers(ycnr_ctx* c, int kind, int32_t from, int32_t to, const int32_t* const* rows, int64_t lim_rows,
+                         std::vector<PortionPre>& pre) {
+  const double t0 = c->trace ? now_ms() : 0.0;
+  constexpr int kPer = 8;
+  const int n = to - from;
+  const std::function<void(int)> fn = [&](int blk) {
+    const int i1 = std::min<int>(to, from + (blk + 1) * kPer);
+    for (int i = from + blk * kPer; i < i1; ++i)
+      if (rows[i]) pre[i] = scan_header(kind, rows[i], lim_rows);
+  };
+  c->pool.run((n + kPer - 1) / kPer, fn);
+  if (c->trace) c->t_scan += now_ms() - t0;
+}
+
 int ycnr_als_portions(ycnr_ctx* c, int32_t n, const int32_t* const* rows, const int32_t* const* indx,
                       const float* const* vals, ycnr_portion_info* infos) {
   if (!c || n < 0 || (n && (!rows || !indx || !vals))) return fail("ycnr_als_portions: bad argument");
-  for (int i = 0; i < n; ++i) OK(ycnr_als_portion(c, rows[i], indx[i], vals[i], infos ? infos + i : nullptr));
-  return 0;
+  if (c->step_type != YCNR_BY_USER && c->step_type != YCNR_BY_ITEM)
+    return fail("ycnr_als_portion: call ycnr_start_train_step first");
+  const int solved_w = c->step_type == YCNR_BY_USER ? YCNR_USER_FACTORS : YCNR_ITEM_FACTORS;
+  std::vector<PortionPre> pre((size_t)n);
+  int rc = 0;
+  for (int g0 = 0; g0 < n && !rc; g0 += kScanGroup) {
+    const int g1 = std::min<int>(n, g0 + kScanGroup);
+    scan_headers(c, 1, g0, g1, rows, c->fac_rows[solved_w], pre);
+    for (int i = g0; i < g1 && !rc; ++i)
+      rc = als_portion_impl(c, rows[i], indx[i], vals[i], infos ? infos + i : nullptr, &pre[i]);
+  }
+  const int rf = run_fill_tasks(c);
+  return rc ? rc : rf;
 }
 
 int ycnr_rmse_portions_async(ycnr_ctx* c, int32_t n, const int32_t* const* rows, const int32_t* const* indx,
                              const float* const* vals, const int64_t* tags) {
   if (!c || n < 0 || (n && (!rows || !indx || !vals))) return fail("ycnr_rmse_portions_async: bad argument");
-  for (int i = 0; i < n; ++i) OK(ycnr_rmse_portion_async(c, rows[i], indx[i], vals[i], tags ? tags[i] : i));
-  return 0;
+  const double t0 = now_ms();
+  std::vector<PortionPre> pre((size_t)n);
+  int rc = 0;
+  for (int g0 = 0; g0 < n && !rc; g0 += kScanGroup) {
+    const int g1 = std::min<int>(n, g0 + kScanGroup);
+    scan_headers(c, 2, g0, g1, rows, c->fac_rows[YCNR_USER_FACTORS], pre);
+    for (int i = g0; i < g1 && !rc; ++i)
+      rc = rmse_portion_async_impl(c, rows[i], indx[i], vals[i], tags ? tags[i] : i, &pre[i]);
+  }
+  const int rf = run_fill_tasks(c);
+  c->t_rmse_calls += now_ms() - t0;
+  return rc ? rc : rf;
 }
 
 // Compatibility export (upstream never calls it from lib/).  When `fixed` is one of the attached
