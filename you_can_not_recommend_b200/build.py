@@ -19,7 +19,7 @@ HOST_LIB = os.path.join(PKG_DIR, "libycnr_host.so")
 CUDA_LIB = os.path.join(PKG_DIR, "libycnr_als.so")
 
 CUDA_SOURCES = ["ycnr_als.cu"]
-CUDA_HEADERS = ["als_kernels.cuh", "row_ldlt.cuh", "rmse_kernels.cuh", "common.cuh", "gram_tc.cuh", "portion_kernels.cuh", "recommend_kernels.cuh", "ingest_kernels.cuh"]
+CUDA_HEADERS = ["als_kernels.cuh", "rmse_kernels.cuh", "common.cuh", "gram_tc.cuh", "portion_kernels.cuh", "recommend_kernels.cuh", "ingest_kernels.cuh"]
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -23,7 +23,6 @@
 // fixed order by MODE_REDUCE, so results do not depend on scheduling.
 #pragma once
 #include "common.cuh"
-#include "row_ldlt.cuh"
 
 #ifndef YCNR_DUAL_FFMA2
 #define YCNR_DUAL_FFMA2 1
@@ -486,100 +485,6 @@ __global__ void __launch_bounds__(NT) als_solve_blocks_kernel(const SolveBlocksA
 }
 
 // ------------------------------------------------------------------------------------
-// k x k solve with the rows in registers (row_ldlt.cuh): sums the tile partials of a row's slices in slice order,
-// adds the ridge and solves by LDL^T.  NW warps, warp q owns rows H q .. H q + H - 1 (H = ceil(k / NW) <= 32),
-// NSEG 16-column segments of registers per row (16 NSEG >= k).  kt: tile rows of the partial format (the Gram
-// kernel's KT).
-// ------------------------------------------------------------------------------------
-template <int NW, int NSEG>
-__global__ void __launch_bounds__(32 * NW) als_solve_rows_kernel(const PrimalArgs a, const int kt) {
-  if (rows_poisoned(a.rows)) return;
-  extern __shared__ __align__(16) float dsm[];
-  const int k = a.k;
-  const int n = k;
-  const int H = (k + NW - 1) / NW;
-  const int GP = row_ldlt_pitch(n);
-  float* Gs = dsm;                                          // G rows, then L columns
-  float* col = Gs + ((n * GP + 128 + 3) & ~3);
-  float* colb = col + 2 * kRowColStride;
-  float* wsm = colb + 2 * kRowColStride;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row = a.work[blockIdx.x];
-  const int first = a.row_first_item[blockIdx.x];
-  const int nit = a.row_n_items[blockIdx.x];
-  const int ntiles = kt * (kt + 1) / 2 + kt;
-  const float* part = a.partial + (size_t)first * ntiles * 16;
-  const size_t pstride = (size_t)ntiles * 16;
-  const float lam = (float)(a.lambda * (double)a.rows.row_len[row]);
-
-  // Stage the summed system as full rows: the partial format keeps the tiles of one tile column (I = L .. kt, the
-  // rhs tile last) contiguous, so a column is one coalesced sweep; tiles below the diagonal are mirrored.
-  for (int L = 0; L < kt; ++L) {
-    const int cnt = (kt - L + 1) * 4;
-    const float* src0 = part + (size_t)tile_linear(L, L, kt) * 16;
-    for (int e = tid; e < cnt; e += 32 * NW) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* src = src0 + 4 * e;
-      for (int it = 0; it < nit; ++it, src += pstride) {
-        const float4 u = *reinterpret_cast<const float4*>(src);
-        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-      }
-      const int I = L + (e >> 2), i = e & 3;
-      const int r = 4 * I + i, c = 4 * L;
-      if (I == kt) {
-        if (i == 0) *reinterpret_cast<float4*>(wsm + c) = v;
-      } else if (r < n) {
-        if (I == L) {
-          if (i == 0) v.x += lam;
-          if (i == 1) v.y += lam;
-          if (i == 2) v.z += lam;
-          if (i == 3) v.w += lam;
-        }
-        const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int jx = 0; jx < 4; ++jx) {
-          if (c + jx < n) {                                  // pad columns of the last tile column: not part of the system
-            Gs[r * GP + c + jx] = vv[jx];
-            if (I > L) Gs[(c + jx) * GP + r] = vv[jx];       // mirror of a tile below the diagonal
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-  const int r = min(H * warp + lane, n - 1);
-  float ra[16 * NSEG];
-  {
-    const float* g = Gs + r * GP;
-    static_for<16 * NSEG>([&](auto cc) { ra[decltype(cc)::value] = g[decltype(cc)::value]; });
-  }
-  const float z = wsm[r];
-  auto sync = [] {
-    if constexpr (NW == 1) __syncwarp();
-    else __syncthreads();
-  };
-  const float w = row_ldlt_forward<NSEG>(n, H, H * warp, lane, col, colb, Gs, GP, ra, z, sync);
-  __syncthreads();   // every z has been read
-  if (lane < H && H * warp + lane < n) wsm[H * warp + lane] = w;
-  __syncthreads();
-  if (warp == 0) {
-    float wv[NW];
-#pragma unroll
-    for (int q = 0; q < NW; ++q) wv[q] = (lane < H && H * q + lane < n) ? wsm[H * q + lane] : 0.f;
-    row_ldlt_backward<NW>(n, H, lane, Gs, GP, wv);
-#pragma unroll
-    for (int q = 0; q < NW; ++q)
-      if (lane < H && H * q + lane < n) wsm[H * q + lane] = wv[q];
-  }
-  __syncthreads();
-  const int rowId = a.rows.row_ids[row];
-  for (int c = tid; c < k; c += 32 * NW) {
-    const float x = wsm[c];
-    for (int d = 0; d < a.dst.n; ++d) a.dst.p[d][(size_t)rowId * k + c] = x;
-  }
-}
-
-// ------------------------------------------------------------------------------------
 // Dual kernel: rows with n <= 4*MT_MAX ratings, n x n system  G = Y Y^T + lambda*n I.
 // ------------------------------------------------------------------------------------
 struct DualArgs {
@@ -1004,281 +909,6 @@ __global__ void __launch_bounds__(NT) als_dual_tpt_kernel(const DualArgs a) {
     }
   } else {
     for (int c = tid; c < k; c += NT) {
-      float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-      const float* yc = Y + c;
-      for (int s2 = 0; s2 < np; s2 += 4) {
-        x0 = fmaf(yc[(s2 + 0) * pitch], vs[s2 + 0], x0);
-        x1 = fmaf(yc[(s2 + 1) * pitch], vs[s2 + 1], x1);
-        x2 = fmaf(yc[(s2 + 2) * pitch], vs[s2 + 2], x2);
-        x3 = fmaf(yc[(s2 + 3) * pitch], vs[s2 + 3], x3);
-      }
-      const float x = (x0 + x1) + (x2 + x3);
-      for (int d = 0; d < a.dst.n; ++d) a.dst.p[d][(size_t)rowId * k + c] = x;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------
-// Dual kernel, one WARP per system with the matrix ROWS in registers (LDL^T, no tiles in the solve).
-//
-// The tile kernels above spend most of their issue slots in the factorisation, not in the Gram sweep: at
-// n = 48 the 4x4-tile Cholesky executes ~5 K warp instructions for 580 warp-FMAs of useful work (tiles whose
-// column is finished idle inside active warps, two CTA barriers and a panel round trip per tile column).  Here
-// lane r owns rows r, r + 32, (r + 64) of G as registers; step j of a right-looking LDL^T is
-//     publish column j (one STS per owned row) -> __syncwarp -> read the pivot and, 4 columns per broadcast
-//     LDS.128, the column -> one FMA per remaining entry of the owned rows,
-// i.e. 4 * RB FMAs per shared-memory instruction, no divergence, no CTA barrier.  The register index of an entry
-// must be a compile-time constant, so the rows are kept RELATIVE to the current 4-column panel: the last step of
-// a panel writes its results four registers down (the destination of an FMA is free), and the panel loop is an
-// ordinary runtime loop over one unrolled body.  Row block b only needs columns <= 32 b + 31 (lower triangle by
-// block), the bound is warp-uniform.  The forward substitution rides along (one FMA per owned row and step),
-// L is parked in shared memory column by column for the back substitution (lane r reads L[j][r] with an odd
-// pitch, x_j comes by shuffle).  The Gram tiles are computed exactly as in the tile kernels (4x4 register tiles,
-// packed fma.f32x2, in-warp K-split while there are at most 16 tiles) and handed to the row owners through
-// shared memory.  Pivots use MUFU.RCP (LDL^T needs no square roots).
-// ------------------------------------------------------------------------------------
-// floats of dynamic shared memory for systems of mt tile rows
-__host__ __device__ constexpr int dual_warp_smem_floats(int mt, int pitch, int rb) {
-  return 4 * mt * (pitch + 32 * rb + 1) + 4 * 32 * rb + 4 * mt + 4;
-}
-
-template <int RB>
-__global__ void __launch_bounds__(32) als_dual_warp_kernel(const DualArgs a) {
-  constexpr int NR = 32 * RB;           // rows a warp can hold
-  constexpr int GP = NR + 1;            // pitch of the G / L staging (odd: column reads are conflict-free)
-  constexpr int TOT = 16 * RB * (RB + 1);
-  if (rows_poisoned(a.rows)) return;
-  extern __shared__ __align__(16) float dsm[];
-  const int lane = threadIdx.x;
-  const int k = a.k, pitch = a.pitch;
-  const int K4 = (k + 3) & ~3;
-  const int row = a.work[blockIdx.x];
-  const int64_t beg = a.rows.row_start[row];
-  const int n = a.rows.row_len[row];
-  const int mt = (n + 3) >> 2;
-  const int np = 4 * mt;
-  float* Y = dsm;                        // [np][pitch], rating r in slot (r & 3) * mt + (r >> 2)
-  float* GL = Y + np * pitch;            // [np][GP]: G row-major, then L column-major
-  float* col = GL + np * GP;             // [2][NR] published column (double-buffered)
-  float* colb = col + 2 * NR;            // [2][NR] published right-hand side
-  float* vs = colb + 2 * NR;             // [np] z in slot order
-  const uint32_t bar = smem_u32(vs + np);
-
-  // ---- gather ------------------------------------------------------------------------------
-  const bool bulk = (k & 3) == 0;
-  if (bulk) {
-    if (lane == 0) {
-      tma_mbar_init(bar, 1);
-      tma_mbar_expect_tx(bar, (uint32_t)n * (uint32_t)k * 4u);
-    }
-    const int CH = k >> 2;
-    for (int q = lane; q < (np - n) * CH; q += 32) {
-      const int r = n + q / CH, c = q % CH;
-      *reinterpret_cast<float4*>(Y + ((r & 3) * mt + (r >> 2)) * pitch + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncwarp();
-    for (int r = lane; r < n; r += 32) {
-      const int cid = __ldg(a.rows.indx + beg + r);
-      tma_bulk_g2s(Y + ((r & 3) * mt + (r >> 2)) * pitch, a.fixed + (size_t)cid * k, (uint32_t)k * 4u, bar);
-    }
-  } else {
-    for (int q = lane; q < np * K4; q += 32) {
-      const int r = q / K4, c = q - r * K4;
-      const bool ok = r < n && c < k;
-      const int cid = ok ? __ldg(a.rows.indx + beg + r) : 0;
-      cp_async4(Y + ((r & 3) * mt + (r >> 2)) * pitch + c, a.fixed + (size_t)cid * k + (ok ? c : 0), ok ? 4 : 0);
-    }
-  }
-  float bb[RB], dinv[RB];
-#pragma unroll
-  for (int b = 0; b < RB; ++b) {
-    const int r = 32 * b + lane;
-    bb[b] = r < n ? __ldg(a.rows.vals + beg + r) : 0.f;
-    dinv[b] = 0.f;
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  if (bulk) tma_mbar_wait(bar, 0);
-  __syncwarp();
-
-  // ---- G = Y Y^T + lambda n I, tile by tile, into shared memory ------------------------------
-  {
-    const float lam = (float)(a.lambda * (double)n);
-    const int ntri = mt * (mt + 1) / 2;
-    int gs = 1;
-    if (ntri <= 16) gs = min(32 / ntri, kDualMaxSplit);
-    const int tstride = mt * pitch;
-    const int CHT = K4 >> 2;
-    for (int base = 0; base < ntri; base += 32) {
-      int g = 0, t = base + lane;
-      if (gs > 1) { g = lane / ntri; t = lane - g * ntri; }
-      const bool active = gs > 1 ? g < gs : t < ntri;
-      int L = 0, rem = active ? t : 0;
-      while (rem >= mt - L) { rem -= mt - L; ++L; }
-      const int I = L + rem;
-      float2 acc2[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
-      if (active) {
-        const float* ya = Y + I * pitch;
-        const float* yb = Y + L * pitch;
-        const int c_beg = 4 * ((g * CHT) / gs), c_end = 4 * (((g + 1) * CHT) / gs);
-#pragma unroll 2
-        for (int c = c_beg; c < c_end; c += 4) {
-          float4 av[4], bv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            av[i] = *reinterpret_cast<const float4*>(ya + i * tstride + c);
-            bv[i] = *reinterpret_cast<const float4*>(yb + i * tstride + c);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 s = acc2[i][j];
-              s = __ffma2_rn(make_float2(av[i].x, av[i].y), make_float2(bv[j].x, bv[j].y), s);
-              s = __ffma2_rn(make_float2(av[i].z, av[i].w), make_float2(bv[j].z, bv[j].w), s);
-              acc2[i][j] = s;
-            }
-        }
-      }
-      const bool own = active && g == 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v = acc2[i][j].x + acc2[i][j].y;
-          if (gs > 1) {   // warp-uniform: the owner adds the partial tiles in group order
-            const float part = v;
-            v = 0.f;
-            for (int gg = 0; gg < gs; ++gg) v += __shfl_sync(0xffffffffu, part, (own ? t : 0) + gg * ntri);
-          }
-          if (own) {
-            const int r = 4 * I + i, c = 4 * L + j;
-            if (r == c && r < n) v += lam;
-            GL[r * GP + c] = v;
-            if (I != L) GL[c * GP + r] = v;
-          }
-        }
-    }
-  }
-  __syncwarp();
-
-  // ---- rows into registers --------------------------------------------------------------------
-  float A[TOT];
-  static_for<RB>([&](auto bc) {
-    constexpr int b = decltype(bc)::value;
-    const int r = 32 * b + lane;
-    const float* g = GL + r * GP;
-    static_for<32 * (b + 1)>([&](auto cc) {
-      constexpr int c = decltype(cc)::value;
-      A[16 * b * (b + 1) + c] = (r < np && c < np) ? g[c] : 0.f;
-    });
-  });
-  __syncwarp();   // G is consumed: its place takes L
-
-  // ---- right-looking LDL^T with the forward substitution, panels of 4 columns --------------------
-  for (int P4 = 0; P4 < n; P4 += 4) {
-    static_for<4>([&](auto jc) {
-      constexpr int jj = decltype(jc)::value;
-      const int j = P4 + jj;
-      if (j < n) {
-        float* cb = col + (jj & 1) * NR;
-        float* cbb = colb + (jj & 1) * NR;
-        static_for<RB>([&](auto bc) {
-          constexpr int b = decltype(bc)::value;
-          if (32 * b + 31 >= P4) {
-            cb[32 * b + lane] = A[16 * b * (b + 1) + jj];
-            cbb[32 * b + lane] = bb[b];
-          }
-        });
-        __syncwarp();
-        const float inv = rcp_fast(cb[j]);
-        const float bj = cbb[j];
-        float t[RB];
-        static_for<RB>([&](auto bc) {
-          constexpr int b = decltype(bc)::value;
-          const int r = 32 * b + lane;
-          t[b] = A[16 * b * (b + 1) + jj] * inv;
-          if (r > j) {
-            bb[b] = fmaf(-t[b], bj, bb[b]);
-            GL[j * GP + r] = t[b];
-          }
-          if (r == j) dinv[b] = inv;
-        });
-        static_for<8 * RB>([&](auto qc) {
-          constexpr int q = decltype(qc)::value;
-          if constexpr (4 * q + 3 > jj) {
-            if (P4 + 4 * q < n) {
-              const float4 cv4 = *reinterpret_cast<const float4*>(cb + P4 + 4 * q);
-              const float cv[4] = {cv4.x, cv4.y, cv4.z, cv4.w};
-              static_for<RB>([&](auto bc) {
-                constexpr int b = decltype(bc)::value;
-                if constexpr (4 * q < 32 * (b + 1)) {
-                  if (P4 + 4 * q <= 32 * b + 31) {
-                    static_for<4>([&](auto ec) {
-                      constexpr int e = decltype(ec)::value;
-                      constexpr int i = 4 * q + e;
-                      if constexpr (i > jj) {
-                        constexpr int dst = jj == 3 ? i - 4 : i;
-                        A[16 * b * (b + 1) + dst] = fmaf(-t[b], cv[e], A[16 * b * (b + 1) + i]);
-                      }
-                    });
-                  }
-                }
-              });
-            }
-          }
-        });
-      }
-    });
-  }
-  __syncwarp();
-
-  // ---- D^-1, then L^T x = w right-looking from the last row: x_j by shuffle, L[j][r] from shared memory -----
-  float w[RB];
-#pragma unroll
-  for (int b = 0; b < RB; ++b) w[b] = bb[b] * dinv[b];
-  for (int j = n - 1; j > 0; --j) {
-    float ws = w[0];
-#pragma unroll
-    for (int b = 1; b < RB; ++b)
-      if ((j >> 5) == b) ws = w[b];
-    const float xj = __shfl_sync(0xffffffffu, ws, j & 31);
-#pragma unroll
-    for (int b = 0; b < RB; ++b) {
-      const int r = 32 * b + lane;
-      if (r < j && 32 * b < j) w[b] = fmaf(-GL[r * GP + j], xj, w[b]);
-    }
-  }
-#pragma unroll
-  for (int b = 0; b < RB; ++b) {
-    const int p = 32 * b + lane;
-    if (p < np) vs[(p & 3) * mt + (p >> 2)] = p < n ? w[b] : 0.f;
-  }
-  __syncwarp();
-
-  // ---- x = Y^T z ------------------------------------------------------------------------------
-  const int rowId = a.rows.row_ids[row];
-  if ((k & 3) == 0) {
-    for (int c4 = lane; c4 < (k >> 2); c4 += 32) {
-      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-      const float* yc = Y + 4 * c4;
-#pragma unroll 2
-      for (int s2 = 0; s2 < np; s2 += 2) {
-        const float4 y0 = *reinterpret_cast<const float4*>(yc + (s2 + 0) * pitch);
-        const float4 y1 = *reinterpret_cast<const float4*>(yc + (s2 + 1) * pitch);
-        const float z0 = vs[s2], z1 = vs[s2 + 1];
-        x0.x = fmaf(y0.x, z0, x0.x); x0.y = fmaf(y0.y, z0, x0.y); x0.z = fmaf(y0.z, z0, x0.z); x0.w = fmaf(y0.w, z0, x0.w);
-        x1.x = fmaf(y1.x, z1, x1.x); x1.y = fmaf(y1.y, z1, x1.y); x1.z = fmaf(y1.z, z1, x1.z); x1.w = fmaf(y1.w, z1, x1.w);
-      }
-      const float4 x = make_float4(x0.x + x1.x, x0.y + x1.y, x0.z + x1.z, x0.w + x1.w);
-      for (int d = 0; d < a.dst.n; ++d) *reinterpret_cast<float4*>(a.dst.p[d] + (size_t)rowId * k + 4 * c4) = x;
-    }
-  } else {
-    for (int c = lane; c < k; c += 32) {
       float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
       const float* yc = Y + c;
       for (int s2 = 0; s2 < np; s2 += 4) {

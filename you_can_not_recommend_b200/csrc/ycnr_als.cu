@@ -505,12 +505,6 @@ struct ycnr_ctx {
   // are then a few waves each; measured on B200: ML-1M shape 1.30 -> 1.04 ms per iteration, MAL 53.2 -> 52.3 ms),
   // YCNR_SPREAD_BULK=0/1 forces it.  Overlapped launches make the per-class event times overlap as well.
   int spread_bulk = -1;
-  // dual bins (bit mt - 1) that run the warp-per-system row-register kernel (als_dual_warp_kernel) instead of the
-  // tile kernels; YCNR_DUAL_WARP=<hex mask> overrides
-  uint32_t dual_warp_mask = 0u;   // experiment, off: slower than the tile kernels
-  // k x k solves (k <= 128) by the row-register LDL^T kernel (als_solve_rows_kernel) instead of the tile Cholesky;
-  // YCNR_SOLVE_ROWS=0/1 overrides
-  bool solve_rows = false;       // experiment, off: 30 ms against 9 ms for the tile Cholesky
   WorkPool pool;
   std::vector<FillTask> fill_tasks;   // deferred header writes of the open batch (multi-portion entry points)
   double t_parse = 0, t_slot_wait = 0, t_copy_issue = 0, t_launch = 0, t_add = 0, t_rmse_calls = 0, t_fill = 0, t_scan = 0;
@@ -703,25 +697,6 @@ int launch_gram_tc(ycnr_ctx* c, const ycnr::PrimalArgs& pa, int item_from, int n
   }
 }
 
-// reduce + solve of `rows` split rows by the row-register LDL^T kernel (kt: tile rows of the partial format)
-template <int NW, int NSEG>
-int launch_solve_rows_cfg(ycnr_ctx* c, const ycnr::PrimalArgs& a, int kt, int rows, cudaStream_t st) {
-  using namespace ycnr;
-  const size_t smem = (size_t)row_ldlt_smem_floats(a.k) * sizeof(float);
-  if (smem > 48 * 1024) OK(ensure_dynamic_smem(c, reinterpret_cast<const void*>(&als_solve_rows_kernel<NW, NSEG>), smem));
-  als_solve_rows_kernel<NW, NSEG><<<rows, 32 * NW, smem, st>>>(a, kt);
-  CU(cudaGetLastError());
-  return 0;
-}
-int launch_solve_rows(ycnr_ctx* c, const ycnr::PrimalArgs& a, int kt, int rows, cudaStream_t st) {
-  const int k = a.k;
-  if (k <= 32) return launch_solve_rows_cfg<1, 2>(c, a, kt, rows, st);
-  if (k <= 64) return launch_solve_rows_cfg<2, 4>(c, a, kt, rows, st);
-  if (k <= 96) return launch_solve_rows_cfg<4, 6>(c, a, kt, rows, st);
-  if (k <= 112) return launch_solve_rows_cfg<4, 7>(c, a, kt, rows, st);
-  return launch_solve_rows_cfg<4, 8>(c, a, kt, rows, st);
-}
-
 template <int KT, int NT>
 int launch_primal_kt(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p, const int32_t* plan_base) {
   using namespace ycnr;
@@ -759,8 +734,7 @@ int launch_primal_kt(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p
           r.row_first_item = a.row_first_item + m0;
           r.row_n_items = a.row_n_items + m0;
           ProfScope ps(c, YCNR_K_REDUCE_SOLVE, m1 - m0, 0, c->aux_stream);
-          if (c->solve_rows) OK(launch_solve_rows(c, r, KT, m1 - m0, c->aux_stream));
-          else als_primal_kernel<KT, NT, 1, MODE_REDUCE><<<m1 - m0, NT, 0, c->aux_stream>>>(r);
+          als_primal_kernel<KT, NT, 1, MODE_REDUCE><<<m1 - m0, NT, 0, c->aux_stream>>>(r);
         }
       }
       c->aux_pending = true;
@@ -774,8 +748,7 @@ int launch_primal_kt(ycnr_ctx* c, const ycnr::PrimalArgs& base, const DevPlan& p
       ProfScope ps(c, YCNR_K_REDUCE_SOLVE, p.n_multi, 0);
       constexpr int RT = YCNR_REDUCE_TPT;                                   // tiles per thread of the solve
       constexpr int RNT = (((NTILES + RT - 1) / RT) + 31) & ~31;
-      if (c->solve_rows) OK(launch_solve_rows(c, a, KT, p.n_multi, c->stream));
-      else als_primal_kernel<KT, RNT, RT, MODE_REDUCE><<<p.n_multi, RNT, 0, c->stream>>>(a);
+      als_primal_kernel<KT, RNT, RT, MODE_REDUCE><<<p.n_multi, RNT, 0, c->stream>>>(a);
     }
   }
   CU(cudaGetLastError());
@@ -937,25 +910,9 @@ int launch_dual_bin2(ycnr_ctx* c, const ycnr::DualArgs& base, int count, int64_t
   return 0;
 }
 
-template <int RB>
-int launch_dual_warp(ycnr_ctx* c, const ycnr::DualArgs& base, int mt, int count, int64_t ratings, const int32_t* work,
-                     cudaStream_t st) {
-  using namespace ycnr;
-  if (count <= 0) return 0;
-  DualArgs a = base;
-  a.work = work;
-  const size_t smem = (size_t)dual_warp_smem_floats(mt, a.pitch, RB) * sizeof(float) + 16;
-  if (smem > 48 * 1024) OK(ensure_dynamic_smem(c, reinterpret_cast<const void*>(&als_dual_warp_kernel<RB>), smem));
-  ProfScope ps(c, YCNR_K_DUAL_FUSED, count, ratings, st, mt - 1);
-  als_dual_warp_kernel<RB><<<count, 32, smem, st>>>(a);
-  CU(cudaGetLastError());
-  return 0;
-}
-
 template <int MT>
 int launch_dual_bin_any(ycnr_ctx* c, const ycnr::DualArgs& d, int count, int64_t ratings, const int32_t* work,
                         cudaStream_t st) {
-  if (c->dual_warp_mask >> (MT - 1) & 1u) return launch_dual_warp<(4 * MT + 31) / 32>(c, d, MT, count, ratings, work, st);
   if constexpr (MT >= YCNR_DUAL2_MIN_MT) return launch_dual_bin2<MT>(c, d, count, ratings, work, st);
   else return launch_dual_bin<MT, dual_nt(MT)>(c, d, count, ratings, work, st);
 }
@@ -1947,8 +1904,6 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
     if (const char* e = getenv("YCNR_HOST_THREADS")) threads = std::max(1, std::min(64, atoi(e)));
     c->pool.start(threads - 1);
   }
-  if (const char* e = getenv("YCNR_DUAL_WARP")) c->dual_warp_mask = (uint32_t)strtoul(e, nullptr, 16);
-  if (const char* e = getenv("YCNR_SOLVE_ROWS")) c->solve_rows = atoi(e) != 0;
   c->fac_rows[0] = o->total_users;
   c->fac_rows[1] = o->total_items;
   CU(cudaSetDevice(o->device));
