@@ -159,6 +159,25 @@ def pipe_peaks():
         return {"tf32_tflops": 1100.0, "ffma_tflops": 56.0, "source": "fallback (B200_PROFILING.md nominal dense tf32)"}
 
 
+def smem_term(k, ratings_per_launch, n_mma, per_launch_ms, sm_count=148, sm_mhz=1965.0):
+    """Shared-memory bandwidth term of gram_tc: executed bytes through the SM's shared memory
+    per launch — LSU wavefronts per rating measured by ncu (profiles/gram_tc_smem.json) plus the tensor core's own
+    operand reads — at 128 B/clk/SM.  Not an algorithmic figure: it explains why the kernel stops at ~0.55 of HBM."""
+    try:
+        p = json.load(open(os.path.join(ROOT, "profiles", "gram_tc_smem.json")))
+        if int(p["k"]) != k:
+            return None
+        lsu = float(p["lsu_wavefronts_per_rating"]) * float(p["wavefront_bytes"])
+        mma = (128 + n_mma) * 4.0
+        peak_gbs = float(p["smem_bytes_per_clk_per_sm"]) * sm_count * sm_mhz * 1e6 / 1e9
+        t = ratings_per_launch * (lsu + mma) / (peak_gbs * 1e9) * 1e3
+        return {"executed_bytes_per_rating": {"lsu_wavefronts": lsu, "mma_operand_reads": mma}, "peak_gbs": peak_gbs,
+                "ms_at_peak": t, "frac": t / per_launch_ms,
+                "source": "profiles/gram_tc_smem.json (ncu wavefront count) + operand footprint; 128 B/clk/SM x %d SMs x %.0f MHz" % (sm_count, sm_mhz)}
+    except Exception:
+        return None
+
+
 def measured_traffic(workload, k, cls):
     """DRAM bytes per launch of kernel class `cls` from the committed ncu --set full capture
     (profiles/traffic_<workload>.json, written by scripts/gpu_round_evidence.sh + DESIGN.md §5); None when
@@ -382,6 +401,7 @@ def main():
             kv = kp if k <= 124 else 2 * {3: 44}.get((k + 59) // 60, 52 if ((k + 59) // 60) * 52 >= k else 60)
             exec_flops = ratings_per_launch * 2.0 * 128 * 2 * ((kv + 4 + 7) // 8 * 8)
             pipe, pipe_peak = "tensor (tcgen05 kind::tf32)", pk["tf32_tflops"]
+            n_mma = 2 * ((kv + 4 + 7) // 8 * 8)
         else:
             exec_flops = ratings_per_launch * 2.0 * (kp * (kp + 4) / 2 + kp)
             pipe, pipe_peak = "fp32 ffma", pk["ffma_tflops"]
@@ -410,6 +430,10 @@ def main():
                                "achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
                                "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                                "note": "gathered factor bytes of both half-steps on rank 0 / iteration time (RMSE passes included in the time) / HBM peak"}}
+        if dom == "gram_tc":
+            st = smem_term(k, ratings_per_launch, n_mma, per_launch_ms)
+            if st:
+                roof["terms"]["smem"] = st
     kernels = {c: {"ms_per_step": prof[c]["ms"] / args.steps, "launches_per_step": prof[c]["launches"] / args.steps,
                    "rows_per_step": prof[c]["rows"] / args.steps, "ratings_per_step": prof[c]["ratings"] / args.steps}
                for c in native.KERNEL_CLASSES if prof[c]["launches"]}

@@ -225,8 +225,11 @@ struct PrimalArgs {
   int fixed_rows;
 };
 
+#ifndef YCNR_REDUCE_MIN_CTAS
+#define YCNR_REDUCE_MIN_CTAS 1
+#endif
 template <int KT, int NT, int TPT, int MODE>
-__global__ void __launch_bounds__(NT) als_primal_kernel(const PrimalArgs a) {
+__global__ void __launch_bounds__(NT, (MODE == MODE_REDUCE ? YCNR_REDUCE_MIN_CTAS : 1)) als_primal_kernel(const PrimalArgs a) {
   constexpr int KP = 4 * KT;          // padded system size
   constexpr int PITCH = KP + 4;       // + (val, 0, 0, 0): the rhs tile row reads its "a" operand here
   constexpr int NTRI = KT * (KT + 1) / 2;
