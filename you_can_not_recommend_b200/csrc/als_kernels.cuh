@@ -225,11 +225,19 @@ struct PrimalArgs {
   int fixed_rows;
 };
 
+// Register cap of the k x k solve (MODE_REDUCE): minimum CTAs per SM handed to __launch_bounds__; 0 = leave it to
+// the compiler (80 registers, 4 CTAs of 192 threads).  Default 5 with three tiles per thread (68 registers).  NB: an explicit 1 lets ptxas spend registers freely and costs
+// occupancy (measured: 8.9 -> 12.5 ms per MAL iteration).
 #ifndef YCNR_REDUCE_MIN_CTAS
-#define YCNR_REDUCE_MIN_CTAS 1
+#define YCNR_REDUCE_MIN_CTAS 5
+#endif
+#if YCNR_REDUCE_MIN_CTAS > 0
+#define YCNR_PRIMAL_BOUNDS(NT, MODE) __launch_bounds__(NT, (MODE == MODE_REDUCE ? YCNR_REDUCE_MIN_CTAS : 1))
+#else
+#define YCNR_PRIMAL_BOUNDS(NT, MODE) __launch_bounds__(NT)
 #endif
 template <int KT, int NT, int TPT, int MODE>
-__global__ void __launch_bounds__(NT, (MODE == MODE_REDUCE ? YCNR_REDUCE_MIN_CTAS : 1)) als_primal_kernel(const PrimalArgs a) {
+__global__ void YCNR_PRIMAL_BOUNDS(NT, MODE) als_primal_kernel(const PrimalArgs a) {
   constexpr int KP = 4 * KT;          // padded system size
   constexpr int PITCH = KP + 4;       // + (val, 0, 0, 0): the rhs tile row reads its "a" operand here
   constexpr int NTRI = KT * (KT + 1) / 2;
@@ -711,6 +719,8 @@ __global__ void __launch_bounds__(NT) als_dual_kernel(const DualArgs a) {
 // thread it is paid 3 times and the CTAs are small enough for more systems to be resident per SM.
 // MT is exact (the host bins rows by tile-row count).
 // ------------------------------------------------------------------------------------
+// (a register cap through __launch_bounds__ min-CTAs was measured for the multi-warp bins — 112 / 100 / 88 registers
+//  instead of 129: dual rows 15.9 -> 17.4 / 17.4 / 19.7 ms per MAL iteration; the tiles spill — not kept)
 template <int MT, int NT, int TPT>
 __global__ void __launch_bounds__(NT) als_dual_tpt_kernel(const DualArgs a) {
   constexpr int NMAX = 4 * MT;

@@ -27,7 +27,7 @@
 #include "rmse_kernels.cuh"
 
 #ifndef YCNR_REDUCE_TPT
-#define YCNR_REDUCE_TPT 2
+#define YCNR_REDUCE_TPT 3   // with YCNR_REDUCE_MIN_CTAS = 5: 8.4 ms against 9.0 ms for 2 tiles / 80 registers (MAL, two runs each)
 #endif
 
 namespace {
