@@ -225,19 +225,18 @@ struct PrimalArgs {
   int fixed_rows;
 };
 
-// Register cap of the k x k solve (MODE_REDUCE): minimum CTAs per SM handed to __launch_bounds__; 0 = leave it to
-// the compiler (80 registers, 4 CTAs of 192 threads).  Default 5 with three tiles per thread (68 registers).  NB: an explicit 1 lets ptxas spend registers freely and costs
-// occupancy (measured: 8.9 -> 12.5 ms per MAL iteration).
+// Occupancy hint of the k x k solve (MODE_REDUCE) with three tiles per thread (128 threads at k = 100): at least
+// YCNR_REDUCE_MIN_CTAS CTAs per SM (5 -> at most 102 registers): 8.5 ms per MAL iteration against 9.0 ms for two
+// tiles per thread (192 threads) at the compiler's own 80 registers.  Other shapes return 0 = unspecified.
+// NB: an explicit 1 lets ptxas spend registers freely and costs occupancy (8.9 -> 12.5 ms).
 #ifndef YCNR_REDUCE_MIN_CTAS
 #define YCNR_REDUCE_MIN_CTAS 5
 #endif
-#if YCNR_REDUCE_MIN_CTAS > 0
-#define YCNR_PRIMAL_BOUNDS(NT, MODE) __launch_bounds__(NT, (MODE == MODE_REDUCE ? YCNR_REDUCE_MIN_CTAS : 1))
-#else
-#define YCNR_PRIMAL_BOUNDS(NT, MODE) __launch_bounds__(NT)
-#endif
+constexpr int primal_min_ctas(int kt, int /*nt*/, int tpt, int mode) {
+  return (mode == 2 && tpt == 3 && kt <= 25) ? YCNR_REDUCE_MIN_CTAS : 0;
+}
 template <int KT, int NT, int TPT, int MODE>
-__global__ void YCNR_PRIMAL_BOUNDS(NT, MODE) als_primal_kernel(const PrimalArgs a) {
+__global__ void __launch_bounds__(NT, primal_min_ctas(KT, NT, TPT, MODE)) als_primal_kernel(const PrimalArgs a) {
   constexpr int KP = 4 * KT;          // padded system size
   constexpr int PITCH = KP + 4;       // + (val, 0, 0, 0): the rhs tile row reads its "a" operand here
   constexpr int NTRI = KT * (KT + 1) / 2;
