@@ -386,7 +386,9 @@ def main():
         if c == "dual_fused" and prof[c]["launches"]:
             return prof[c]["ms"] / max(1.0, prof[c]["launches"] / (args.steps or 1))
         return prof[c]["ms"] / (args.steps or 1)
-    dom = max(native.KERNEL_CLASSES, key=kernel_ms)
+    # (classes that carry no ratings of their own — the k x k solve reads tile partials — cannot be put against a
+    #  per-rating roofline; they stay in `kernels`)
+    dom = max((c for c in native.KERNEL_CLASSES if prof[c]["ratings"] > 0), key=kernel_ms, default=max(native.KERNEL_CLASSES, key=kernel_ms))
     roof = None
     pk = pipe_peaks()
     if prof[dom]["launches"] > 0 and prof[dom]["ms"] > 0:
@@ -422,7 +424,7 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": alg_flops,
                 "terms": {"hbm": {"ms_at_peak": t_hbm, "peak_gbs": peak, "frac": t_hbm / per_launch_ms},
                           "pipe": {"pipe": pipe, "executed_flops_per_launch": exec_flops, "peak_tflops": pipe_peak,
-                                   "executed_over_algorithmic": exec_flops / alg_flops, "ms_at_peak": t_pipe,
+                                   "executed_over_algorithmic": exec_flops / alg_flops if alg_flops else None, "ms_at_peak": t_pipe,
                                    "frac": t_pipe / per_launch_ms, "peak_source": pk["source"]}},
                 "roofline_ms": max(t_hbm, t_pipe), "frac_of_max_term": max(t_hbm, t_pipe) / per_launch_ms,
                 "share_of_step": prof[dom]["ms"] / ms if ms > 0 else None,

@@ -20,7 +20,10 @@ except Exception as e:
     print(" no line:", e)
 PY
 }
+python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1 || tail -20 $O/build.log
 run mal --no-cpu --e2e-python-steps 0
 run netflix --workload netflix --no-cpu --e2e-python-steps 0 --e2e-large-portion 0
-run mal_k256 --factors 256 --no-cpu --no-e2e --steps 3 --warmup 2
-run mal_k128 --factors 128 --no-cpu --no-e2e --steps 3 --warmup 2
+if [ "${2:-}" = "wide" ]; then
+  run mal_k256 --factors 256 --no-cpu --no-e2e --steps 3 --warmup 2
+  run mal_k128 --factors 128 --no-cpu --no-e2e --steps 3 --warmup 2
+fi

@@ -35,6 +35,8 @@ napi_status napi_get_value_bool(napi_env, napi_value, bool*);
 napi_status napi_get_value_int64(napi_env, napi_value, int64_t*);
 napi_status napi_create_array(napi_env, napi_value*);
 napi_status napi_set_element(napi_env, napi_value object, uint32_t index, napi_value value);
+napi_status napi_get_element(napi_env, napi_value object, uint32_t index, napi_value* result);
+napi_status napi_get_array_length(napi_env, napi_value value, uint32_t* result);
 napi_status napi_get_named_property(napi_env, napi_value object, const char* name, napi_value* result);
 napi_status napi_has_named_property(napi_env, napi_value object, const char* name, bool* result);
 napi_status napi_set_named_property(napi_env, napi_value object, const char* name, napi_value value);

@@ -17,6 +17,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <vector>
+
 #include "ycnr_als.h"
 
 namespace {
@@ -211,6 +213,63 @@ napi_value RmsePortionAsync(napi_env env, napi_callback_info info) {
     return nullptr;
   if (!check(env, ycnr_check_portion(rows, (int64_t)n0, (int64_t)n1, (int64_t)n2))) return nullptr;
   check(env, ycnr_rmse_portion_async(c, rows, indx, vals, tag));
+  return undefined(env);
+}
+
+// Portion buffers of a whole half-step / RMSE pass handed over at once (the master's portion cache,
+// usePortionsCache: EmfMaster.js:434-494): three JS arrays of typed arrays -> pointer tables for
+// ycnr_als_portions / ycnr_rmse_portions_async, which scan and queue the headers with the library's host threads.
+bool portion_tables(napi_env env, napi_value rows_a, napi_value indx_a, napi_value vals_a, std::vector<const int32_t*>& rows,
+                    std::vector<const int32_t*>& indx, std::vector<const float*>& vals) {
+  uint32_t n = 0, n1 = 0, n2 = 0;
+  if (napi_get_array_length(env, rows_a, &n) != napi_ok || napi_get_array_length(env, indx_a, &n1) != napi_ok ||
+      napi_get_array_length(env, vals_a, &n2) != napi_ok || n1 != n || n2 != n)
+    return fail(env, "portion arrays of different lengths");
+  rows.resize(n); indx.resize(n); vals.resize(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    napi_value r, x, v;
+    int32_t *pr, *pi;
+    float* pv;
+    size_t l0, l1, l2;
+    if (napi_get_element(env, rows_a, i, &r) != napi_ok || napi_get_element(env, indx_a, i, &x) != napi_ok ||
+        napi_get_element(env, vals_a, i, &v) != napi_ok || !typed(env, r, napi_int32_array, &pr, &l0) ||
+        !typed(env, x, napi_int32_array, &pi, &l1) || !typed(env, v, napi_float32_array, &pv, &l2))
+      return false;
+    if (!check(env, ycnr_check_portion(pr, (int64_t)l0, (int64_t)l1, (int64_t)l2))) return false;
+    rows[i] = pr; indx[i] = pi; vals[i] = pv;
+  }
+  return true;
+}
+
+// alsPortions(handle, [alsRows...], [alsIndx...], [alsVals...]) -> [completedPortion fields per portion]
+napi_value AlsPortions(napi_env env, napi_callback_info info) {
+  napi_value a[4];
+  ycnr_ctx* c;
+  std::vector<const int32_t*> rows, indx;
+  std::vector<const float*> vals;
+  if (!args(env, info, 4, a) || !handle(env, a[0], &c) || !portion_tables(env, a[1], a[2], a[3], rows, indx, vals)) return nullptr;
+  std::vector<ycnr_portion_info> infos(rows.size() ? rows.size() : 1);
+  if (!check(env, ycnr_als_portions(c, (int32_t)rows.size(), rows.data(), indx.data(), vals.data(), infos.data()))) return nullptr;
+  napi_value arr;
+  napi_create_array(env, &arr);
+  for (size_t i = 0; i < rows.size(); ++i) napi_set_element(env, arr, (uint32_t)i, portion_result(env, infos[i], false));
+  return arr;
+}
+
+// rmsePortionsAsync(handle, [rmseRows...], [rmseIndx...], [rmseVals...], firstPortionNo): portion i is queued under
+// tag firstPortionNo + i; the sums come back from rmsePoll
+napi_value RmsePortionsAsync(napi_env env, napi_callback_info info) {
+  napi_value a[5];
+  ycnr_ctx* c;
+  int64_t first = 0;
+  std::vector<const int32_t*> rows, indx;
+  std::vector<const float*> vals;
+  if (!args(env, info, 5, a) || !handle(env, a[0], &c) || !portion_tables(env, a[1], a[2], a[3], rows, indx, vals) ||
+      napi_get_value_int64(env, a[4], &first) != napi_ok)
+    return nullptr;
+  std::vector<int64_t> tags(rows.size());
+  for (size_t i = 0; i < rows.size(); ++i) tags[i] = first + (int64_t)i;
+  check(env, ycnr_rmse_portions_async(c, (int32_t)rows.size(), rows.data(), indx.data(), vals.data(), tags.data()));
   return undefined(env);
 }
 
@@ -464,6 +523,8 @@ napi_value Init(napi_env env, napi_value exports) {
       {"attachFactors", nullptr, AttachFactors, nullptr, nullptr, nullptr, 0, nullptr},
       {"startTrainStep", nullptr, StartTrainStep, nullptr, nullptr, nullptr, 0, nullptr},
       {"alsPortion", nullptr, AlsPortion, nullptr, nullptr, nullptr, 0, nullptr},
+      {"alsPortions", nullptr, AlsPortions, nullptr, nullptr, nullptr, 0, nullptr},
+      {"rmsePortionsAsync", nullptr, RmsePortionsAsync, nullptr, nullptr, nullptr, 0, nullptr},
       {"endTrainStep", nullptr, EndTrainStep, nullptr, nullptr, nullptr, 0, nullptr},
       {"startCalcRmse", nullptr, StartCalcRmse, nullptr, nullptr, nullptr, 0, nullptr},
       {"rmsePortion", nullptr, RmsePortion, nullptr, nullptr, nullptr, 0, nullptr},
