@@ -374,6 +374,19 @@ class EmfMaster(EmfBase):
             self.rSum += msg["rSum"]
             self._lastRmseMsg = msg
 
+    def wm_completedPortions(self, tags, infos):
+        """m_completedPortion for all replies of a pass at once (the native multi-portion path): the same additions
+        in the same (queue) order — np.cumsum adds sequentially — and the same 'last message' (quirk Q7)."""
+        n = len(tags)
+        if n == 0:
+            return
+        self.completedPortions += n
+        self.rSumDiff2 = float(np.cumsum(np.concatenate(([self.rSumDiff2], infos["r_sum_diff2"])))[-1])
+        self.rCnt = float(np.cumsum(np.concatenate(([self.rCnt], infos["r_cnt"])))[-1])
+        self.rSum = float(np.cumsum(np.concatenate(([self.rSum], infos["r_sum"])))[-1])
+        self._lastRmseMsg = {"portionNo": int(tags[-1]), "rSumDiff2": float(infos["r_sum_diff2"][-1]),
+                             "rCnt": float(infos["r_cnt"][-1]), "rSum": float(infos["r_sum"][-1])}
+
     def _gatherRmseShift0(self):
         """world > 1, bulk: 'rmseSaveCalcs' (EmfMaster.js:726-736) for the validate AND the test pass in one
         all-gather — sums at shift 0 plus the sum of the ratings, with which every rank derives the pass at any
@@ -437,9 +450,7 @@ class EmfMaster(EmfBase):
             if cache is not None and self.options["gpu"].get("nativeLoop", False):
                 prep = self._preparedPortions(stepType, "rmse", lo, hi)
                 self.ctx.rmse_portions_async(prep)
-                for tag, info in self.ctx.rmse_poll(True):
-                    self.wm_completedPortion({"portionNo": int(tag), "rSumDiff2": info.r_sum_diff2, "rCnt": info.r_cnt,
-                                              "rSum": info.r_sum})
+                self.wm_completedPortions(*self.ctx.rmse_poll_arrays(True))
                 self.h2d_bytes += prep["h2d"]
                 self.d2h_bytes += 24 * prep["n"]
                 lo = hi

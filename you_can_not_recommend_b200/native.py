@@ -221,6 +221,29 @@ class Context:
             if n.value < max_out:
                 return out
 
+    _PORTION_DTYPE = None
+
+    def rmse_poll_arrays(self, wait=False, max_out=4096):
+        """The same as rmse_poll, as arrays: (tags int64[n], infos structured[n] with the PortionInfo fields) — what a
+        binding hands to a master that accumulates a whole pass at once (EmfMaster.wm_completedPortions)."""
+        import numpy as np
+        if Context._PORTION_DTYPE is None:
+            Context._PORTION_DTYPE = np.dtype([("rows_from", "<i4"), ("rows_cnt", "<i4"), ("ratings_in_portion", "<i8"),
+                                               ("time_ms", "<f8"), ("r_sum_diff2", "<f8"), ("r_cnt", "<f8"), ("r_sum", "<f8")])
+            assert Context._PORTION_DTYPE.itemsize == C.sizeof(PortionInfo)
+        tags_all, infos_all = [], []
+        while True:
+            tags = np.empty(max_out, dtype=np.int64)
+            infos = np.empty(max_out, dtype=Context._PORTION_DTYPE)
+            n = C.c_int32(0)
+            _check(lib().ycnr_rmse_poll(self._h, C.c_int32(int(wait)), C.c_int32(max_out), tags.ctypes.data_as(C.POINTER(C.c_int64)),
+                                        infos.ctypes.data_as(C.POINTER(PortionInfo)), C.byref(n)))
+            tags_all.append(tags[:n.value])
+            infos_all.append(infos[:n.value])
+            if n.value < max_out:
+                break
+        return (np.concatenate(tags_all), np.concatenate(infos_all)) if len(tags_all) > 1 else (tags_all[0], infos_all[0])
+
     @staticmethod
     def _ptr_array(arrays, ctype):
         return (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
