@@ -505,6 +505,7 @@ struct ycnr_ctx {
   // are then a few waves each; measured on B200: ML-1M shape 1.30 -> 1.04 ms per iteration, MAL 53.2 -> 52.3 ms),
   // YCNR_SPREAD_BULK=0/1 forces it.  Overlapped launches make the per-class event times overlap as well.
   int spread_bulk = -1;
+  bool spread_batch = true;   // batches of small portions: dual bins on the bin streams (YCNR_SPREAD_BATCH=0: in stream order)
   WorkPool pool;
   std::vector<FillTask> fill_tasks;   // deferred header writes of the open batch (multi-portion entry points)
   double t_parse = 0, t_slot_wait = 0, t_copy_issue = 0, t_launch = 0, t_add = 0, t_rmse_calls = 0, t_fill = 0, t_scan = 0;
@@ -1764,7 +1765,7 @@ int batch_flush(ycnr_ctx* c) {
     OK(launch_validate_cols(c, view.indx, off, c->fac_rows[1 - solved]));
     if (R > 0) {
       const double tl0 = now_ms();
-      OK(run_als(c, c->step_type, view, plan, (const int32_t*)(d + o_plan), true));
+      OK(run_als(c, c->step_type, view, plan, (const int32_t*)(d + o_plan), c->spread_batch));
       c->t_launch += now_ms() - tl0;
       if (c->h_fac[solved] && c->h_registered[solved]) {
         // solved rows back to the host segment under the next batch's kernels; portions whose id ranges touch
@@ -1898,6 +1899,7 @@ int ycnr_create(const ycnr_options* o, ycnr_ctx** out) {
   c->trace = getenv("YCNR_TRACE") != nullptr;
   if (const char* e = getenv("YCNR_BATCH_FLUSH")) c->batch_flush_ratings = std::max<int64_t>(1, atoll(e));
   if (const char* e = getenv("YCNR_SPREAD_BULK")) c->spread_bulk = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("YCNR_SPREAD_BATCH")) c->spread_batch = atoi(e) != 0;
   {   // host threads of the multi-portion entry points (the caller is one of them)
     const int hw = (int)std::thread::hardware_concurrency();
     int threads = std::max(1, std::min(6, hw / 4));
