@@ -10,7 +10,7 @@
 using namespace ycnr;
 
 template <int N>
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, float* sink) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, float* sink, int mode) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
   uint64_t* bar = reinterpret_cast<uint64_t*>(base + 8 * 4096);
@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, float* sink
   for (int i = tid; i < 8 * 4096 / 4; i += 128) reinterpret_cast<float*>(base)[i] = 1.0f + (float)(i % 97) * 0.013f;
   if (tid == 0) {
     mbar_init(smem_u32(bar), 1);
+    mbar_init(smem_u32(bar + 1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -45,9 +46,14 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, float* sink
           " @q tcgen05.mma.cta_group::1.kind::tf32 [%0], d0, d0, %3, t;\n"
           " @q tcgen05.mma.cta_group::1.kind::tf32 [%0], d1, d1, %3, t;\n"
           " @q tcgen05.mma.cta_group::1.kind::tf32 [%0], d2, d2, %3, t;\n"
-          " @q tcgen05.mma.cta_group::1.kind::tf32 [%0], d3, d3, %3, t;\n}\n" ::"r"(tmem + (uint32_t)((it & 1) * 256)),
+          " @q tcgen05.mma.cta_group::1.kind::tf32 [%0], d3, d3, %3, t;\n}\n" ::"r"(tmem + (uint32_t)(((mode & 1) ? 0 : (it & 1)) * 256)),
           "r"(lo), "r"(hi), "r"(IDESC)
           : "memory");
+      if (mode & 2)   // a commit per group of four MMAs onto a second mbarrier nobody waits for (the Gram kernel's per-stage commit)
+        asm volatile(
+            "{\n .reg .pred q;\n elect.sync _|q, 0xffffffff;\n"
+            " @q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar + 1))
+            : "memory");
     }
     asm volatile(
         "{\n .reg .pred q;\n elect.sync _|q, 0xffffffff;\n"
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, float* sink
 }
 
 template <int N>
-double run(int sms, int iters) {
+double run(int sms, int iters, int mode = 0) {
   const size_t smem = 8 * 4096 + 64 + 1024;
   cudaFuncSetAttribute(mma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaEvent_t e0, e1;
@@ -71,7 +77,7 @@ double run(int sms, int iters) {
   float ms = 0;
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
-    mma_rate_kernel<N><<<sms, 128, smem>>>(iters, nullptr);
+    mma_rate_kernel<N><<<sms, 128, smem>>>(iters, nullptr, mode);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(&ms, e0, e1);
@@ -88,5 +94,13 @@ int main() {
   cudaError_t e = cudaDeviceSynchronize();
   printf("{\"tf32_mma_tflops_n256\": %.1f, \"tf32_mma_tflops_n208\": %.1f, \"sms\": %d, \"status\": \"%s\"}\n", t256, t208, sms,
          cudaGetErrorString(e));
+  // clocks per MMA instruction (at the nominal 1.965 GHz) for the shapes and issue patterns of the Gram kernel:
+  // mode bit 0: ONE accumulator (every MMA depends on the previous one), bit 1: a tcgen05.commit per four MMAs
+  for (int mode = 0; mode < 4; ++mode) {
+    const double r208 = run<208>(sms, iters, mode), r144 = run<144>(sms, iters, mode), r80 = run<80>(sms, iters, mode), r48 = run<48>(sms, iters, mode);
+    auto clk = [&](double tflops, int n) { return 2.0 * 128 * n * 8 / (tflops * 1e12 / sms / 1.965e9); };
+    printf("{\"mode\": %d, \"clk_per_mma\": {\"n208\": %.1f, \"n144\": %.1f, \"n80\": %.1f, \"n48\": %.1f}}\n", mode, clk(r208, 208),
+           clk(r144, 144), clk(r80, 80), clk(r48, 48));
+  }
   return 0;
 }
