@@ -73,7 +73,7 @@ constexpr int kTcPrefetchUses = 2;                            // L2 prefetch dis
 constexpr int kTcSmemLimit = 232448;                          // 227 KB per CTA on sm_100
 // Measured on B200 (MAL, k = 100): 6 stages x 32 ratings 27.3 ms per iteration, 12 x 16 ratings 28.2 ms —
 // the ring is not latency-bound per slot, the shared-memory pipe is the limiter.
-constexpr int kTcMaxStages = 9;    // one loader + two splitter warps per slot: 160 + 96 x 9 = 1024 threads
+constexpr int kTcMaxStages = 6;
 
 template <int KT>
 struct TcCfg {
@@ -83,11 +83,11 @@ struct TcCfg {
   static constexpr int N = 2 * NC;             // MMA N
   static constexpr int NPAN = (N + 31) / 32 < 4 ? 4 : (N + 31) / 32;   // A reads 4 panels (M = 128)
   static constexpr int STAGE_BYTES = NPAN * kTcPanelBytes;
-  // epilogue staging: the strict upper triangle of X, transposed (Xt[c (c - 1) / 2 + r] = X[r][c], r < c)
-  static constexpr int XS_BYTES = (NC * (NC - 1) / 2 * 4 + 15) & ~15;
+  static constexpr int XP = NC | 1;            // odd pitch: conflict-free row-per-thread stores
+  static constexpr int XS_BYTES = (NC * XP * 4 + 15) & ~15;
   static constexpr int STAGES_FIT = (kTcSmemLimit - 2048 - XS_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT < kTcMaxStages ? STAGES_FIT : kTcMaxStages;
-  static constexpr int THREADS = kTcEpiThreads + 32 + 3 * 32 * STAGES;   // epilogue | MMA | 1 loader + 2 splitters per slot
+  static constexpr int THREADS = kTcEpiThreads + 32 + 4 * 32 * STAGES;   // epilogue | MMA | 2 loaders + 2 splitters per slot
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + XS_BYTES + (3 * STAGES + 4) * 8 + 16 + 1024;
   static_assert(KP + 4 <= 128, "rhs column must fit the M = 128 accumulator");
   static_assert(NCH <= 32, "one lane per 16-byte chunk of a rating");
@@ -127,34 +127,14 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(bar) : "memory");
 }
-// YCNR_TC_WAIT_HINT > 0: suspend-time hint (ns) of mbarrier.try_wait — the waiting warp may stay suspended that long
-// before the instruction returns false, i.e. fewer polls from the ~25 warps of the CTA that are waiting at any time;
-// YCNR_TC_WAIT_SLEEP > 0: nanosleep between polls
-#ifndef YCNR_TC_WAIT_HINT
-#define YCNR_TC_WAIT_HINT 0
-#endif
-#ifndef YCNR_TC_WAIT_SLEEP
-#define YCNR_TC_WAIT_SLEEP 0
-#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
-#if YCNR_TC_WAIT_HINT > 0
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"((uint32_t)YCNR_TC_WAIT_HINT)
-        : "memory");
-#else
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
-#endif
-#if YCNR_TC_WAIT_SLEEP > 0
-    if (!ok) __nanosleep(YCNR_TC_WAIT_SLEEP);
-#endif
   } while (!ok);
 }
 
@@ -231,7 +211,7 @@ struct TcItemIter {
 template <int KT>
 __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __grid_constant__ GramTcArgs a) {
   using Cfg = TcCfg<KT>;
-  constexpr int NCH = Cfg::NCH, NC = Cfg::NC;
+  constexpr int NCH = Cfg::NCH, NC = Cfg::NC, XP = Cfg::XP;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NTRI = KT * (KT + 1) / 2;
   constexpr int NTILES = NTRI + KT;
@@ -241,7 +221,7 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __
 
   if (rows_poisoned(a.rows)) return;   // uniform for the whole grid: nothing has been allocated yet
   extern __shared__ __align__(1024) uint8_t tc_smem[];
-  // carve: [stages][STAGE_BYTES] | Xs (strict upper triangle of X, transposed) | barriers | tmem base
+  // carve: [stages][STAGE_BYTES] | Xs[NC][XP] | barriers | tmem base
   // SWIZZLE_128B atoms are addressed by absolute shared-memory bits [7,10): align the ring to 1024 B
   uint8_t* stage_base = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
   float* Xs = reinterpret_cast<float*>(stage_base + STAGES * Cfg::STAGE_BYTES);
@@ -260,9 +240,9 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, 2);     // two splitter warps
       mbar_init(empty0 + 8 * s, 1);
-      // cp.async path: every lane of the slot's loader warp arrives when its copies have landed;
-      // TMA path: one arrive.expect_tx by the loader warp, the copy engine completes the bytes
-      mbar_init(raw0 + 8 * s, a.use_tma ? 1 : 32);
+      // cp.async path: every lane of the two loader warps arrives when its copies have landed;
+      // TMA path: one arrive.expect_tx per loader warp, the copy engine completes the bytes
+      mbar_init(raw0 + 8 * s, a.use_tma ? 2 : 64);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf0 + 8 * b, 1);
@@ -289,9 +269,8 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __
     // four LDS.128 in flight in the splitter shortens the cycle; the slots stay in order per warp.
     constexpr int HR = kTcStageRows / 2;
     const int pw = warp - 5;
-    const bool loader = pw < STAGES;
-    // one loader warp per ring slot (the whole stage), two splitter warps per slot (one half = HR ratings each)
-    const int s_own = loader ? pw : (pw - STAGES) >> 1, half = loader ? 0 : (pw - STAGES) & 1;
+    const bool loader = pw < 2 * STAGES;
+    const int s_own = (loader ? pw : pw - 2 * STAGES) >> 1, half = pw & 1;
     const int k = a.k;
     // lane = 16-byte chunk of a rating (lanes 0..KT-1: factors, lane KT: the rating value).
     // Offsets of that chunk for the four values of r % 4 (the swizzle phase); + (r / 4) * 512.
@@ -301,20 +280,20 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __
       oh4[j] = tc_chunk_offset(j, 4 * min(lane, NCH - 1));
       ol4[j] = tc_chunk_offset(j, NC + 4 * min(lane, NCH - 1));
     }
-    uint8_t* const sb = stage_base + s_own * Cfg::STAGE_BYTES + half * (HR / 4) * 512;   // splitters: this warp's half of the slot
+    uint8_t* const sb = stage_base + s_own * Cfg::STAGE_BYTES + half * (HR / 4) * 512;   // this warp's half of the slot
     TcItemIter ix;
     ix.init(a);
     ix.advance(a, s_own);
     if (loader) {
       // ============================ loaders ============================
-      // lane r: column id of rating r of the stage under the iterator
+      // lane r < HR: column id of rating half*HR + r of the stage under the iterator
       auto load_ids = [&](const TcItemIter& x, int& col, uint32_t& vm, int64_t& e0) {
         col = 0;
         e0 = 0;
         bool ok = false;
         if (x.valid(a)) {
-          e0 = x.seg_beg + (int64_t)x.st * kTcStageRows;
-          ok = x.st * kTcStageRows + lane < x.seg_len;
+          e0 = x.seg_beg + (int64_t)x.st * kTcStageRows + half * HR;
+          ok = lane < HR && x.st * kTcStageRows + half * HR + lane < x.seg_len;
           if (ok) col = __ldg(a.rows.indx + e0 + lane);
         }
         vm = __ballot_sync(0xffffffffu, ok);
@@ -322,42 +301,41 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __
       const int src_col = lane < a.chunks_a ? a.col_a + 4 * lane : a.col_b + 4 * (lane - a.chunks_a);
       const float* src_lane = a.fixed + src_col;
       const bool lane_ok = lane < KT && src_col < k;
-      const uint32_t val_off = tc_chunk_offset(lane, 4 * KT);
+      const uint32_t val_off = tc_chunk_offset(lane & (HR - 1), 4 * KT);
       auto issue = [&](uint32_t use, int col, uint32_t vm, int64_t e0) {
         mbar_wait(empty0 + 8 * s_own, (use & 1u) ^ 1u);
-#pragma unroll 8
-        for (int r = 0; r < kTcStageRows; ++r) {
+#pragma unroll
+        for (int r = 0; r < HR; ++r) {
           const int c = __shfl_sync(0xffffffffu, col, r);
           const bool ok = ((vm >> r) & 1u) && lane_ok;
           if (lane < KT) cp_async16(sb + oh4[r & 3] + (r >> 2) * 512, src_lane + (size_t)c * k, ok ? 16 : 0);
         }
-        {   // the rating values: lane r -> column KP of rating r, (val, 0, 0, 0)
+        if (lane < HR) {   // the rating values: lane r -> column KP of rating r, (val, 0, 0, 0)
           const bool ok = (vm >> lane) & 1u;
           cp_async4(sb + val_off, a.rows.vals + (ok ? e0 + lane : 0), ok ? 4 : 0);
         }
         // this lane's arrival on the stage's raw barrier fires when its copies have landed
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(raw0 + 8 * s_own) : "memory");
       };
-      // TMA variant of issue(): lane l lands the atom (group g = l / 4 of four ratings, panel p = l % 4).
+      // TMA variant of issue(): lane l < 16 lands the atom (group g = l / 4 of four ratings, panel p = l % 4).
       const bool tma = a.use_tma != 0;
       const int hp = (k + 31) >> 5;                     // panels that hold real columns
       const uint64_t tmap_addr = reinterpret_cast<uint64_t>(&a.tmap);
       auto issue_tma = [&](uint32_t use, int col, uint32_t vm) {
         mbar_wait(empty0 + 8 * s_own, (use & 1u) ^ 1u);
-        const int g = lane >> 2, p = lane & 3;
+        const int g = (lane >> 2) & 3, p = lane & 3;
         int ir[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c = __shfl_sync(0xffffffffu, col, 4 * g + q);
           ir[q] = ((vm >> (4 * g + q)) & 1u) ? c : a.fixed_rows;      // out-of-range row: zero-filled by the copy engine
         }
-        const bool skip_copy = (a.variant & 128u) != 0;   // diagnostics only (wrong numbers): no gather at all
         if (lane == 0)
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(raw0 + 8 * s_own),
-                       "r"(skip_copy ? 0u : (uint32_t)(8 * hp * 512))
+                       "r"((uint32_t)(4 * hp * 512))
                        : "memory");
         __syncwarp();
-        if (p < hp && !skip_copy)
+        if (lane < 16 && p < hp)
           asm volatile(
               "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(
                   smem_u32(sb + p * kTcPanelBytes + g * 512)),
@@ -365,35 +343,32 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __
               : "memory");
       };
       // L2 prefetch of the rows this warp will gather kTcPrefetchUses ring cycles from now: the bytes in
-      // flight against HBM latency are no longer capped by the ring's shared memory.  Lane l asks for the four
-      // 128-byte lines at +0, +128, +256, +384 of rating l: a 400-byte row that starts on a 16-byte boundary
-      // touches exactly those.
+      // flight against HBM latency are no longer capped by the ring's shared memory (6 x 32 ratings x 400 B).
+      // Lane l asks for 128-byte line (l >> 4) and (l >> 4) + 2 of rating l & 15: a 400-byte row that starts
+      // on a 16-byte boundary touches exactly the 4 lines at +0, +128, +256, +384.
       const bool do_pf = a.prefetch != 0;
       TcItemIter px = ix;
       if (do_pf) px.advance(a, kTcPrefetchUses * STAGES);
       auto load_pf_ids = [&](const TcItemIter& x, int& col) {
         col = -1;
         if (x.valid(a)) {
-          if (x.st * kTcStageRows + lane < x.seg_len)
-            col = __ldg(a.rows.indx + x.seg_beg + (int64_t)x.st * kTcStageRows + lane);
+          const int rr = half * HR + (lane & (HR - 1));
+          if (x.st * kTcStageRows + rr < x.seg_len)
+            col = __ldg(a.rows.indx + x.seg_beg + (int64_t)x.st * kTcStageRows + rr);
         }
       };
       const bool one_range = a.chunks_a >= KT;
       auto prefetch_rows = [&](int col) {
         if (col >= 0) {
           if (one_range) {
-            const char* p = reinterpret_cast<const char*>(a.fixed + (size_t)col * k);
-#pragma unroll
-            for (int o = 0; o < 512; o += 128)
-              if (o < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p + o));
+            const char* p = reinterpret_cast<const char*>(a.fixed + (size_t)col * k) + (lane >> 4) * 128;
+            if ((lane >> 4) * 128 < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+            if ((lane >> 4) * 128 + 256 < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p + 256));
           } else {   // two column ranges of at most 240 bytes: two lines each (the lines they start in and the next)
             const char* row = reinterpret_cast<const char*>(a.fixed + (size_t)col * k);
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              const int oa = a.col_a * 4 + h2 * 128, ob = a.col_b * 4 + h2 * 128;
-              if (oa < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + oa));
-              if (ob < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + ob));
-            }
+            const int oa = a.col_a * 4 + (lane >> 4) * 128, ob = a.col_b * 4 + (lane >> 4) * 128;
+            if (oa < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + oa));
+            if (ob < k * 4) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + ob));
           }
         }
       };
@@ -442,7 +417,7 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __
         }
         mbar_wait(raw0 + 8 * s_own, use & 1u);
         if (a.variant & 32u) {   // diagnostics only (wrong numbers): no tail split — what the kernel costs without it
-          if (!(a.variant & 512u)) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(full0 + 8 * s_own);
           continue;
@@ -477,7 +452,7 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __
             }
           }
         }
-        if (!(a.variant & 512u)) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // (512: diagnostics, unsafe)
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(full0 + 8 * s_own);
       }
@@ -516,12 +491,7 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint32_t lo = desc_lo0 + s * kStageLo;
         const uint32_t bar = empty0 + 8 * s;
-        if ((a.variant & 64u) != 0) {   // diagnostics only (wrong numbers): no MMA, the stage is handed back at once
-          asm volatile(
-              "{\n .reg .pred q;\n elect.sync _|q, 0xffffffff;\n"
-              " @q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar)
-              : "memory");
-        } else if (st < nfull) {
+        if (st < nfull) {
           asm volatile(
               "{\n .reg .pred p, q, t;\n .reg .b32 l1, l2, l3;\n .reg .b64 d0, d1, d2, d3;\n"
               " setp.ne.b32 p, %4, 0;\n setp.eq.b32 t, 0, 0;\n"
@@ -567,19 +537,14 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __
     __syncwarp();
   } else {
     // ============================ epilogue ============================
-    // Thread m owns row m of X = D[:, :NC] + 2 D[:, NC:] (TMEM lane m).  The symmetrised (X + X^T) / 2 is produced
-    // in two passes over the accumulator, with only the strict upper triangle staged in shared memory:
-    //   pass 1: X[m][c], c > m, is parked transposed (Xt[c (c - 1) / 2 + m]: lanes on consecutive addresses);
-    //   pass 2: the row is read from TMEM again and, for c < m, averaged with Xt[m (m - 1) / 2 + c] = X[c][m];
-    //           the thread then holds row m of the lower triangle = row m % 4 of the tiles (m / 4, L <= m / 4) and
-    //           stores them straight from registers (four neighbouring lanes write one 64-byte tile).
-    // Against the round-1 epilogue (full X in shared memory, tiles assembled by strided reads: 37 % bank-conflict
-    // wavefronts) this halves the staging — which is what buys the ring its 7th stage at k = 100 — and drops the
-    // transposed read pass.  Entries right of the diagonal inside a diagonal tile are written unsymmetrised
-    // (X[m][c]): the solvers read the lower triangle of diagonal tiles only (chol4_inverse).
     const int m = tid;  // TMEM lane == row of X; warp w may only touch lanes 32w .. 32w+31
-    const int eI = m >> 2, ei = m & 3;
-    const int tri_m = (m * (m - 1)) / 2;
+    constexpr int EPI_TPT = (NTILES + kTcEpiThreads - 1) / kTcEpiThreads;
+    int eI[EPI_TPT], eL[EPI_TPT];   // this thread's output tiles, the same for every item
+#pragma unroll
+    for (int j = 0; j < EPI_TPT; ++j) {
+      eI[j] = eL[j] = 0;
+      if (tid + j * kTcEpiThreads < NTILES) tile_coords(tid + j * kTcEpiThreads, KT, NTRI, eI[j], eL[j]);
+    }
     uint32_t itc = 0;
     for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
       const uint32_t buf = itc & 1u, aph = (itc >> 1) & 1u;
@@ -587,7 +552,8 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __
       mbar_wait(accf0 + 8 * buf, aph);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16) + buf * 256u;
-      auto load16 = [&](int c0, float (&x)[16]) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < NC; c0 += 16) {
         uint32_t h[16], l[16];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
@@ -600,51 +566,34 @@ __global__ void __launch_bounds__(TcCfg<KT>::THREADS, 1) gram_tc_kernel(const __
               "=r"(l[8]), "=r"(l[9]), "=r"(l[10]), "=r"(l[11]), "=r"(l[12]), "=r"(l[13]), "=r"(l[14]), "=r"(l[15])
             : "r"(taddr + (uint32_t)NC + (uint32_t)c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (m < NC) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = fmaf(2.0f, __uint_as_float(l[j]), __uint_as_float(h[j]));
-      };
-      const bool skip_epi = (a.variant & 256u) != 0;   // diagnostics only (wrong numbers): handshakes without the passes
-      // pass 1 (column blocks that hold entries right of some lane's diagonal: c0 + 15 > 32 w)
-#pragma unroll 1
-      for (int c0 = 0; c0 < NC; c0 += 16) {
-        if (c0 + 15 <= 32 * warp || skip_epi) continue;
-        float x[16];
-        load16(c0, x);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = c0 + j;
-          if (c > m && c < NC) Xs[(c * (c - 1)) / 2 + m] = x[j];
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < NC) Xs[m * XP + c0 + j] = fmaf(2.0f, __uint_as_float(l[j]), __uint_as_float(h[j]));
         }
       }
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      // pass 2 (column blocks that hold entries left of or on some lane's diagonal: c0 <= 32 w + 31)
-      const int it0 = a.item_order ? __ldg(a.item_order + it) : it;   // partials stay indexed by the item itself
-      float* out = a.partial + (size_t)it0 * NTILES * 16;
-#pragma unroll 1
-      for (int c0 = 0; c0 < NC; c0 += 16) {
-        if (c0 > 32 * warp + 31 || skip_epi) break;
-        float x[16];
-        load16(c0, x);
-        if (m < 4 * KT + 4) {      // rows of the system + the rhs tile row (NC may be rounded up beyond them)
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int L = (c0 >> 2) + jj;
-            if (L <= eI && L < KT) {     // tile (eI, L); eI == KT: the rhs tile row
-              float o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = 4 * L + e;
-                o[e] = c < m ? 0.5f * (x[4 * jj + e] + Xs[tri_m + c]) : x[4 * jj + e];
-              }
-              const int t = L * (KT + 1) - (L * (L - 1)) / 2 + (eI - L);   // tile_linear(eI, L, KT)
-              *reinterpret_cast<float4*>(out + (size_t)t * 16 + 4 * ei) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-          }
-        }
-      }
-      // accumulator drained: hand it back to the MMA warp
+      // accumulator drained: hand it back to the MMA warp before the slower smem -> HBM part
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       mbar_arrive(acce0 + 8 * buf);
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      const int it0 = a.item_order ? __ldg(a.item_order + it) : it;   // partials stay indexed by the item itself
+      float* out = a.partial + (size_t)it0 * NTILES * 16;
+#pragma unroll
+      for (int j = 0; j < EPI_TPT; ++j) {
+        const int t = tid + j * kTcEpiThreads;
+        if (t >= NTILES) break;
+        const int I = eI[j], L = eL[j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 o;
+          const int ri = 4 * I + i;
+          o.x = 0.5f * (Xs[ri * XP + 4 * L + 0] + Xs[(4 * L + 0) * XP + ri]);
+          o.y = 0.5f * (Xs[ri * XP + 4 * L + 1] + Xs[(4 * L + 1) * XP + ri]);
+          o.z = 0.5f * (Xs[ri * XP + 4 * L + 2] + Xs[(4 * L + 2) * XP + ri]);
+          o.w = 0.5f * (Xs[ri * XP + 4 * L + 3] + Xs[(4 * L + 3) * XP + ri]);
+          *reinterpret_cast<float4*>(out + (size_t)t * 16 + 4 * i) = o;
+        }
+      }
       asm volatile("bar.sync 1, 128;\n" ::: "memory");   // Xs is rewritten by the next item
     }
   }
