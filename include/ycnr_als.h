@@ -283,6 +283,12 @@ int ycnr_recommend_batch(ycnr_ctx* ctx, int32_t n_users, const int32_t* user_ids
  * item_order inside the packed plan; words_out (may be NULL) receives the packed plan (n_words_out words). */
 int ycnr_debug_plan(const ycnr_options* opts, const int32_t* row_len, int32_t n_rows, int32_t* summary,
                     int32_t* words_out, int64_t cap_words, int64_t* n_words_out);
+/* The row arrays of a batch of portion headers as the multi-portion entry points build them (host code only, no GPU
+ * needed): counts_out[3 n] = entries, ratings, bad flag per portion; ids/len/start receive the concatenated rows
+ * (kind 1) or RMSE work entries of at most 64 ratings (kind 2) of the valid portions; threads = host workers. */
+int ycnr_debug_batch_rows(int32_t kind, int32_t n, const int32_t* const* rows, int64_t lim_rows, int32_t threads,
+                          int64_t* counts_out, int32_t* ids_out, int32_t* len_out, int64_t* start_out, int64_t cap,
+                          int64_t* entries_out);
 /* Copy the tile partials ([items][tiles][16] floats) left by the last split-row launch. */
 int ycnr_debug_read_partials(ycnr_ctx* ctx, float* out, int64_t n_floats);
 

@@ -105,3 +105,52 @@ def test_kernel_resource_usage_fits_the_launch_shapes():
         name = next(f for f in usage if "gram_tc_kernelILi%dE" % kt in f)
         regs = usage[name]["REG"]
         assert ((regs + 7) // 8 * 8) * threads <= 65536, (name, regs, threads)
+
+
+def test_multi_portion_header_scan_and_fill_match_the_per_row_rule():
+    """Host side of ycnr_als_portions / ycnr_rmse_portions_async (no GPU): the worker pool's scan + deferred fill of a
+    batch of portion headers gives, for every thread count, the rows a sequential walk gives — ALS rows as they are,
+    RMSE rows cut into work entries of at most 64 ratings (a zero-length row is one empty entry) with running rating
+    offsets — and flags headers whose ids are not ascending, out of range or whose lengths are negative."""
+    import numpy as np
+    from you_can_not_recommend_b200 import native
+    rng = np.random.default_rng(5)
+    heads, lim = [], 5000
+    for p in range(37):
+        R = int(rng.integers(0, 60))
+        ids = np.sort(rng.choice(lim, R, replace=False)).astype(np.int32)
+        lens = rng.choice([0, 1, 2, 63, 64, 65, 128, 129, 700], R).astype(np.int32)
+        h = np.zeros(2 * R + 1, np.int32)
+        h[0] = R
+        h[1::2], h[2::2] = ids, lens
+        heads.append(h)
+    bad = [heads[3].copy(), heads[5].copy(), heads[7].copy()]
+    if bad[0][0] >= 2:
+        bad[0][3] = bad[0][1]                      # ids not strictly ascending
+    bad[1][2 * int(bad[1][0]) - 1 if bad[1][0] else 0] = lim   # id out of range (R >= 1 with overwhelming probability)
+    if bad[2][0] >= 1:
+        bad[2][2] = -4                             # negative length
+    heads_all = heads + bad
+    for kind in (1, 2):
+        want_ids, want_len, want_start, run = [], [], [], 0
+        for h in heads:
+            for r in range(int(h[0])):
+                i, n = int(h[1 + 2 * r]), int(h[2 + 2 * r])
+                if kind == 1:
+                    want_ids.append(i); want_len.append(n); want_start.append(run); run += n
+                else:
+                    while True:
+                        m = min(n, 64)
+                        want_ids.append(i); want_len.append(m); want_start.append(run)
+                        run += m
+                        n -= m
+                        if n <= 0:
+                            break
+        for threads in (1, 2, 5):
+            counts, ids, ln, st = native.debug_batch_rows(kind, heads_all, lim, threads)
+            assert (counts[:len(heads), 2] == 0).all()
+            assert counts[len(heads) + 0, 2] != 0 or bad[0][0] < 2
+            assert counts[len(heads) + 1, 2] != 0 or bad[1][0] < 1
+            assert counts[len(heads) + 2, 2] != 0 or bad[2][0] < 1
+            assert counts[:len(heads), 1].sum() == run
+            assert ids.tolist() == want_ids and ln.tolist() == want_len and st.tolist() == want_start

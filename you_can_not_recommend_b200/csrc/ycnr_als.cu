@@ -3099,6 +3099,48 @@ int ycnr_debug_plan(const ycnr_options* o, const int32_t* row_len, int32_t n_row
   return 0;
 }
 
+// The row arrays the multi-portion entry points build for a batch of portion headers (host code only, no GPU):
+// scan (entries, ratings, validity per portion) by the worker pool exactly as ycnr_als_portions /
+// ycnr_rmse_portions_async do it, then the deferred fill.  kind 1 = ALS rows, 2 = RMSE work entries of at most 64
+// ratings.  counts_out[3 n]: entries, ratings, bad flag per portion; the arrays receive the concatenated batch
+// (capacity cap entries; portions that are invalid or do not fit are skipped and leave their counts behind).
+int ycnr_debug_batch_rows(int32_t kind, int32_t n, const int32_t* const* rows, int64_t lim_rows, int32_t threads,
+                          int64_t* counts_out, int32_t* ids_out, int32_t* len_out, int64_t* start_out, int64_t cap,
+                          int64_t* entries_out) {
+  if ((kind != 1 && kind != 2) || n < 0 || (n && !rows) || !counts_out || !entries_out) return fail("ycnr_debug_batch_rows: bad argument");
+  WorkPool pool;
+  pool.start(std::max(0, threads - 1));
+  std::vector<PortionPre> pre((size_t)n);
+  constexpr int kPer = 8;
+  const std::function<void(int)> scan = [&](int blk) {
+    const int i1 = std::min<int>(n, (blk + 1) * kPer);
+    for (int i = blk * kPer; i < i1; ++i)
+      if (rows[i]) pre[i] = scan_header(kind, rows[i], lim_rows);
+  };
+  pool.run((n + kPer - 1) / kPer, scan);
+  std::vector<FillTask> tasks;
+  int64_t e = 0, run = 0;
+  for (int i = 0; i < n; ++i) {
+    counts_out[3 * i] = pre[i].entries;
+    counts_out[3 * i + 1] = pre[i].ratings;
+    counts_out[3 * i + 2] = pre[i].bad;
+    if (pre[i].bad || !rows[i] || e + pre[i].entries > cap) continue;
+    tasks.push_back({kind, rows[i], (size_t)e, run});
+    e += pre[i].entries;
+    run += pre[i].ratings;
+  }
+  if (ids_out && len_out && start_out) {
+    const std::function<void(int)> fill = [&](int i) {
+      const FillTask& t = tasks[i];
+      fill_header(t.kind, t.rows, ids_out + t.r0, len_out + t.r0, start_out + t.r0, t.base);
+    };
+    pool.run((int)tasks.size(), fill);
+  }
+  pool.shutdown();
+  *entries_out = e;
+  return 0;
+}
+
 int ycnr_debug_read_partials(ycnr_ctx* c, float* out, int64_t n_floats) {
   if (!c || !out || n_floats < 0) return fail("ycnr_debug_read_partials: bad argument");
   OK(set_device(c));

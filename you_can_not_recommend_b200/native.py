@@ -27,7 +27,7 @@ EXPORTS = [
     "ycnr_check_portion", "ycnr_factor_elems", "ycnr_memory_usage", "ycnr_rowset_create",
     "ycnr_rowset_destroy", "ycnr_als_rowset", "ycnr_rmse_rowset", "ycnr_rmse_rowset_begin", "ycnr_rmse_rowset_ratings", "ycnr_ipc_export", "ycnr_ipc_import",
     "ycnr_ipc_close", "ycnr_set_peers", "ycnr_table_upload", "ycnr_table_split", "ycnr_table_counts", "ycnr_rowset_from_table",
-    "ycnr_rowset_info", "ycnr_rowset_read", "ycnr_recommend_batch", "ycnr_debug_plan", "ycnr_debug_read_partials", "ycnr_profile_reset", "ycnr_profile_read",
+    "ycnr_rowset_info", "ycnr_rowset_read", "ycnr_recommend_batch", "ycnr_debug_plan", "ycnr_debug_batch_rows", "ycnr_debug_read_partials", "ycnr_profile_reset", "ycnr_profile_read",
     "ycnr_profile_dual_bins",
 ]
 
@@ -107,6 +107,22 @@ def debug_plan(row_len, factors_count=100, gram_path=GRAM_AUTO, dual_max_cols=-1
     return {"dual": dual, "fused": words[summ[27]:summ[27] + n_fused].copy(), "multi": words[summ[28]:summ[28] + n_multi].copy(),
             "item_row": words[summ[29]:summ[29] + n_items].copy(), "item_off": words[summ[30]:summ[30] + n_items].copy(),
             "item_order": words[summ[31]:summ[31] + n_items].copy()}
+
+
+def debug_batch_rows(kind, headers, lim_rows, threads=4):
+    """Row arrays (kind 1) / RMSE work entries (kind 2) the multi-portion entry points build from portion headers
+    (CPU only): returns (counts[n, 3] = entries, ratings, bad; ids, len, start of the valid portions)."""
+    n = len(headers)
+    headers = [np.ascontiguousarray(h, np.int32) for h in headers]
+    ptrs = (C.c_void_p * max(n, 1))(*[h.ctypes.data for h in headers])
+    counts = np.zeros((n, 3), np.int64)
+    cap = int(sum(int(h[0]) + int(np.maximum(h[2:2 * int(h[0]) + 1:2], 0).sum()) // 64 + 1 for h in headers if h[0] >= 0)) + 8
+    ids, ln, st = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int64)
+    e = C.c_int64(0)
+    _check(lib().ycnr_debug_batch_rows(C.c_int32(kind), C.c_int32(n), ptrs, C.c_int64(lim_rows), C.c_int32(threads),
+                                       counts.ctypes.data_as(C.POINTER(C.c_int64)), _i32(ids), _i32(ln),
+                                       st.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(cap), C.byref(e)))
+    return counts, ids[:e.value], ln[:e.value], st[:e.value]
 
 
 def build_sub_fixed_facts_noctx(sub, fixed, indx, cols, k):
