@@ -8,7 +8,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from you_can_not_recommend_b200 import build  # noqa: E402
 
-build.build_cuda()
+build.build_cuda(force=bool(os.environ.get("YCNR_NVCC_FLAGS")))
 from you_can_not_recommend_b200 import front_end as fe  # noqa: E402
 from you_can_not_recommend_b200.emf_master import EmfMaster  # noqa: E402
 

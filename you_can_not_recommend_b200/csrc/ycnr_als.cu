@@ -434,7 +434,10 @@ struct ycnr_ctx {
   cudaEvent_t copied = nullptr;
   // per-portion path: the dual bins of a portion are small launches (about one wave each at 8 M ratings);
   // spread over these streams they run concurrently and fill each other's tail waves
-  static constexpr int kBinStreams = 3;
+#ifndef YCNR_BIN_STREAMS
+#define YCNR_BIN_STREAMS 3
+#endif
+  static constexpr int kBinStreams = YCNR_BIN_STREAMS;
   cudaStream_t bin_stream[kBinStreams] = {nullptr};
   cudaEvent_t fork_ev = nullptr, join_ev[kBinStreams] = {nullptr};
   cudaStream_t d2h_stream = nullptr;    // solved rows -> host factor segment, overlaps the next portion
