@@ -173,7 +173,7 @@ def smem_term(k, ratings_per_launch, n_mma, per_launch_ms, sm_count=148, sm_mhz=
         t = ratings_per_launch * (lsu + mma) / (peak_gbs * 1e9) * 1e3
         return {"executed_bytes_per_rating": {"lsu_wavefronts": lsu, "mma_operand_reads": mma}, "peak_gbs": peak_gbs,
                 "ms_at_peak": t, "frac": t / per_launch_ms,
-                "source": "profiles/gram_tc_smem.json (ncu wavefront count) + operand footprint; 128 B/clk/SM x %d SMs x %.0f MHz" % (sm_count, sm_mhz)}
+                "source": "MODEL: profiles/gram_tc_smem.json (ncu LSU wavefront count) + tensor-core operand footprint, assumed to share one 128 B/clk/SM port x %d SMs x %.0f MHz; ncu itself reports the LSU data pipe 79-81 %% busy (DESIGN.md 3.5)" % (sm_count, sm_mhz)}
     except Exception:
         return None
 
