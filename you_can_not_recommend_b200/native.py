@@ -66,6 +66,12 @@ def lib():
     if _lib is None:
         L = C.CDLL(build.build_cuda())
         L.ycnr_last_error.restype = C.c_char_p
+        # per-message entry points: prototypes with plain address arguments, so the hot path passes the arrays'
+        # addresses as ints (numpy's .ctypes.data_as costs ~1.5 us per argument)
+        L.ycnr_check_portion.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64]
+        L.ycnr_als_portion.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ycnr_rmse_portion_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.ycnr_rmse_poll.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -73,6 +79,11 @@ def lib():
 def _check(rc):
     if rc != 0:
         raise RuntimeError("ycnr_als: " + lib().ycnr_last_error().decode())
+
+
+def _addr(a):
+    """Address of a numpy array's first element (int)."""
+    return a.__array_interface__["data"][0]
 
 
 def _i32(a):
@@ -204,8 +215,11 @@ class Context:
 
     def als_portion(self, rows, indx, vals):
         info = PortionInfo()
-        _check(lib().ycnr_check_portion(_i32(rows), C.c_int64(len(rows)), C.c_int64(len(indx)), C.c_int64(len(vals))))
-        _check(lib().ycnr_als_portion(self._h, _i32(rows), _i32(indx), _f32(vals), C.byref(info)))
+        L = lib()
+        ra = _addr(rows)
+        if L.ycnr_check_portion(ra, len(rows), len(indx), len(vals)) or \
+                L.ycnr_als_portion(self._h, ra, _addr(indx), _addr(vals), C.addressof(info)):
+            _check(1)
         return info
 
     def end_train_step(self):
@@ -222,18 +236,24 @@ class Context:
 
     def rmse_portion_async(self, rows, indx, vals, tag):
         """Queue an RMSE portion under `tag`; results come back from rmse_poll in queue order."""
-        _check(lib().ycnr_check_portion(_i32(rows), C.c_int64(len(rows)), C.c_int64(len(indx)), C.c_int64(len(vals))))
-        _check(lib().ycnr_rmse_portion_async(self._h, _i32(rows), _i32(indx), _f32(vals), C.c_int64(tag)))
+        L = lib()
+        ra = _addr(rows)
+        if L.ycnr_check_portion(ra, len(rows), len(indx), len(vals)) or \
+                L.ycnr_rmse_portion_async(self._h, ra, _addr(indx), _addr(vals), tag):
+            _check(1)
 
     def rmse_poll(self, wait=False, max_out=4096):
         """[(tag, PortionInfo)] of completed RMSE portions, oldest first; wait=True flushes and waits for all."""
         out = []
+        buf = getattr(self, "_poll_buf", None)
+        if buf is None or len(buf[0]) != max_out:       # landing arrays are reused: a poll per message must stay cheap
+            buf = self._poll_buf = ((C.c_int64 * max_out)(), (PortionInfo * max_out)(), C.c_int32(0))
+        tags, infos, n = buf
+        L = lib()
         while True:
-            tags = (C.c_int64 * max_out)()
-            infos = (PortionInfo * max_out)()
-            n = C.c_int32(0)
-            _check(lib().ycnr_rmse_poll(self._h, C.c_int32(int(wait)), C.c_int32(max_out), tags, infos, C.byref(n)))
-            out.extend((tags[i], infos[i]) for i in range(n.value))
+            if L.ycnr_rmse_poll(self._h, int(wait), max_out, tags, infos, C.byref(n)):
+                _check(1)
+            out.extend((tags[i], PortionInfo.from_buffer_copy(infos[i])) for i in range(n.value))
             if n.value < max_out:
                 return out
 
