@@ -134,7 +134,9 @@ class EmfWorker(EmfBase):
         (EmfWorker.js:304-314) — is emitted as soon as its sums are back, always in portion order."""
         pb = msg.get("portionBuffer") or self.portionBuffer
         self.ctx.rmse_portion_async(pb["rmseRows"], pb["rmseIndx"], pb["rmseVals"], msg["portionNo"])
-        self._emitCompletedRmse(False)
+        self._rmseQueued = getattr(self, "_rmseQueued", 0) + 1
+        if self._rmseQueued % 8 == 0:            # replies are asynchronous anyway: look for finished portions now and then
+            self._emitCompletedRmse(False)
 
     def mw_endCalcRmse(self, msg=None):
         """Addition (like endTrainStep): the master has handed out the last portion of the pass — flush the
