@@ -496,9 +496,9 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(args.e2e_portion, True, max(1, args.steps), max(1, args.warmup))
         if args.e2e_large_portion and world == 1:      # (a few 8 M-rating portions cannot be balanced over ranks)
-            e2e["large_portions"] = run_e2e(args.e2e_large_portion, False, max(1, min(args.steps, 3)), 1)
+            e2e["large_portions"] = run_e2e(args.e2e_large_portion, False, max(1, min(args.steps, 3)), max(1, args.warmup))
         if args.e2e_python_steps:
-            e2e["python_messages"] = run_e2e(args.e2e_portion, False, args.e2e_python_steps, 1)
+            e2e["python_messages"] = run_e2e(args.e2e_portion, False, args.e2e_python_steps, max(1, min(args.warmup, 2)))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
