@@ -87,10 +87,13 @@ class ClockSampler:
 
     def _poll(self):
         n = self.nvml
+        try:
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)     # constant: asked once
+        except Exception:
+            mx = 0
         while not self.stop_flag:
             try:
                 sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
-                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
                 try:
                     rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                 except Exception:
@@ -98,7 +101,7 @@ class ClockSampler:
                 self.samples.append((sm, mx, rs))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -118,7 +121,7 @@ class ClockSampler:
             reasons = sorted(k for k, b in bits.items() if any(x[2] & b for x in self.samples))
             return {"sm_mhz": statistics.median(sm) if sm else None,
                     "sm_max_mhz": max(x[1] for x in self.samples) if self.samples else None,
-                    "samples": len(sm), "reasons": reasons, "source": "nvml, 4 ms poll"}
+                    "samples": len(sm), "reasons": reasons, "source": "nvml, 2 ms poll"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
